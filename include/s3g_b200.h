@@ -1,0 +1,171 @@
+/*
+ * s3g_b200.h - C ABI of the B200-native differentiable 4D Gaussian splatting
+ * hot path (libs3g_b200.so).
+ *
+ * This is the drop-in boundary for the render path of nnanhuang/S3Gaussian
+ * (SURVEY.md section 8b).  Every entry point takes plain device pointers,
+ * sizes and scalars - no torch types - and replaces one reference interface,
+ * cited as <file>:<line> relative to the reference tree
+ * (DGR = submodules/depth-diff-gaussian-rasterization):
+ *
+ *   s3g_mark_visible        <- CudaRasterizer::Rasterizer::markVisible   DGR/cuda_rasterizer/rasterizer.h:24-29
+ *                              (pybind: _C.mark_visible                  DGR/ext.cpp:18)
+ *   s3g_rasterize_forward   <- CudaRasterizer::Rasterizer::forward       DGR/cuda_rasterizer/rasterizer.h:31-56
+ *                              (pybind: _C.rasterize_gaussians           DGR/ext.cpp:16, DGR/rasterize_points.cu:35-117)
+ *   s3g_rasterize_backward  <- CudaRasterizer::Rasterizer::backward      DGR/cuda_rasterizer/rasterizer.h:58-88
+ *                              (pybind: _C.rasterize_gaussians_backward  DGR/ext.cpp:17, DGR/rasterize_points.cu:119-202)
+ *   s3g_deform_forward /    <- deform_network.forward_dynamic            scene/deformation.py:216-231
+ *   s3g_deform_backward        + HexPlaneField.forward                   scene/hexplane.py:160-183
+ *                              + activations / Python SH->RGB            gaussian_renderer/__init__.py:99-117
+ *
+ * Conventions (identical to the reference):
+ *   - all pointers are DEVICE pointers unless the name says host;
+ *   - 4x4 matrices are 16 floats, m[k] = M[k%4][k/4] (column-major of the
+ *     mathematical matrix, i.e. the transposed torch tensors of scene/cameras.py:59-63);
+ *   - a NULL shs / colors_precomp / scales / rotations / cov3D_precomp selects
+ *     the code path exactly as nullptr does at forward.cu:205,241 and backward.cu:406,410;
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the
+ *     legacy default stream; we take the caller's stream explicitly);
+ *   - every function returns >= 0 on success and a negative S3G_ERR_* code on
+ *     failure; s3g_last_error() returns a thread-local message.
+ *
+ * There is NO CPU fallback anywhere behind this ABI: without a CUDA device every
+ * compute entry point fails with S3G_ERR_CUDA.
+ */
+#ifndef S3G_B200_H
+#define S3G_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3G_ABI_VERSION 1
+
+#define S3G_OK 0
+#define S3G_ERR_ARG (-1)    /* bad argument (maps to the AT_ERROR / Exception paths of the reference glue) */
+#define S3G_ERR_CUDA (-2)   /* a CUDA runtime call or kernel launch failed */
+#define S3G_ERR_ALLOC (-3)  /* an allocator callback returned NULL */
+#define S3G_ERR_STATE (-4)  /* inconsistent opaque buffers passed to backward */
+
+/* Growable byte-arena callback: replaces the three std::function<char*(size_t)>
+ * arguments of Rasterizer::forward (rasterizer.h:32-34, created by
+ * resizeFunctional() at rasterize_points.cu:27-33).  Must return a device
+ * pointer to at least `bytes` bytes, 128-byte aligned or better. */
+typedef char* (*s3g_alloc_fn)(void* user, size_t bytes);
+
+int s3g_abi_version(void);
+const char* s3g_last_error(void);
+/* name of the CUDA arch the kernels were compiled for, e.g. "sm_100a" */
+const char* s3g_build_arch(void);
+
+/* ---- visibility (rasterizer_impl.cu:54-66,141-153) ---------------------- */
+int s3g_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* ---- forward (rasterizer_impl.cu:198-339) -------------------------------
+ * Returns num_rendered (>= 0) like the reference, or a negative error.
+ * out_color [3,H,W], out_depth [1,H,W], radii [P] (may be NULL) are
+ * caller-allocated; the three opaque state buffers are grown through the
+ * callbacks and are the forward->backward contract (their LAYOUT is ours, not
+ * the reference's; use s3g_state_field() to look inside).
+ * One blocking 4-byte D2H read happens inside (as rasterizer_impl.cu:282) to
+ * size the binning arena. */
+int64_t s3g_rasterize_forward(
+    s3g_alloc_fn geom_alloc, void* geom_user,
+    s3g_alloc_fn binning_alloc, void* binning_user,
+    s3g_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    int* radii,
+    int debug,
+    void* stream);
+
+/* ---- backward (rasterizer_impl.cu:343-444) ------------------------------
+ * All dL_* outputs are written for every Gaussian (zeros where radii <= 0), so
+ * the caller need NOT pre-zero them (the reference glue zero-fills ten tensors,
+ * rasterize_points.cu:154-163).  dL_dconic [P,4] and dL_ddepth [P] are the
+ * reference's internal intermediates; pass NULL unless you want them exported
+ * (parity tests do).  dL_dmean2D is [P,3] with z untouched = 0
+ * (backward.cu:578-579). */
+int s3g_rasterize_backward(
+    int P, int D, int M, int64_t R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer,
+    char* binning_buffer,
+    char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_ddepth,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    int debug,
+    void* stream);
+
+/* ---- state-buffer introspection (tests / debugging) ---------------------
+ * buffer: 0 = geometry, 1 = binning, 2 = image.  Looks up a named field of our
+ * layout for the given problem size and returns its byte offset from the
+ * (128-byte aligned) buffer base, its element size and element count.
+ * Fields: geometry: "xyAB","Cod","rgb","depth_key","tiles_touched","rect","clamped"
+ *         binning : "point_list","point_list_tiles"
+ *         image   : "final_T","n_contrib","ranges"
+ * Returns S3G_OK or S3G_ERR_ARG. */
+int s3g_state_field(int buffer, const char* name, int64_t P, int64_t R, int width, int height,
+                    size_t* offset, size_t* elem_bytes, size_t* count);
+
+/* sizes of the three arenas (bytes) for a problem size; R may be 0 */
+size_t s3g_geom_bytes(int64_t P);
+size_t s3g_binning_bytes(int64_t R);
+size_t s3g_image_bytes(int width, int height);
+
+/* ---- standalone device radix sort (exposed for tests) -------------------
+ * Stable LSD sort of n (key,value) u32 pairs on key bits [begin_bit,end_bit).
+ * keys_out/vals_out receive the result; keys_in/vals_in are clobbered; `temp`
+ * must hold s3g_sort_temp_bytes(n) bytes. */
+size_t s3g_sort_temp_bytes(int64_t n);
+int s3g_sort_pairs_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in,
+                       uint32_t* keys_out, uint32_t* vals_out,
+                       int begin_bit, int end_bit, void* temp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3G_B200_H */

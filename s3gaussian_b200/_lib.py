@@ -1,0 +1,79 @@
+"""ctypes binding of libs3g_b200.so (include/s3g_b200.h).
+
+Loading fails loudly when the CUDA library has not been built: there is no CPU
+or eager-PyTorch fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libs3g_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+S3G_OK = 0
+ERR_NAMES = {-1: "S3G_ERR_ARG", -2: "S3G_ERR_CUDA", -3: "S3G_ERR_ALLOC", -4: "S3G_ERR_STATE"}
+
+_lib = None
+
+# every symbol include/s3g_b200.h declares: (name, restype, argtypes)
+_F, _V, _I, _I64, _SZ = C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+SIGNATURES = {
+    "s3g_abi_version": (_I, []),
+    "s3g_last_error": (C.c_char_p, []),
+    "s3g_build_arch": (C.c_char_p, []),
+    "s3g_mark_visible": (_I, [_I, _V, _V, _V, _V, _V]),
+    "s3g_rasterize_forward": (_I64, [ALLOC_FN, _V, ALLOC_FN, _V, ALLOC_FN, _V, _I, _I, _I, _V, _I, _I,
+                                      _V, _V, _V, _V, _V, _F, _V, _V, _V, _V, _V, _F, _F, _I, _V, _V,
+                                      _V, _I, _V]),
+    "s3g_rasterize_backward": (_I, [_I, _I, _I, _I64, _V, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V,
+                                    _V, _F, _F, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
+                                    _V, _V, _V, _I, _V]),
+    "s3g_state_field": (_I, [_I, C.c_char_p, _I64, _I64, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ),
+                             C.POINTER(_SZ)]),
+    "s3g_geom_bytes": (_SZ, [_I64]),
+    "s3g_binning_bytes": (_SZ, [_I64]),
+    "s3g_image_bytes": (_SZ, [_I, _I]),
+    "s3g_sort_temp_bytes": (_SZ, [_I64]),
+    "s3g_sort_pairs_u32": (_I, [_I64, _V, _V, _V, _V, _I, _I, _V, _V]),
+}
+
+
+def load():
+    """Return the loaded library (builds nothing; see s3gaussian_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m s3gaussian_b200.build` "
+            "(nvcc, sm_100a). s3gaussian_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.s3g_abi_version() != 1:
+        raise RuntimeError("libs3g_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().s3g_last_error().decode()
+
+
+def check(code: int, what: str) -> int:
+    """status < 0 -> RuntimeError (the reference glue raises through AT_ERROR / std::runtime_error)."""
+    if code < 0:
+        raise RuntimeError(f"{what}: {ERR_NAMES.get(int(code), code)}: {last_error()}")
+    return code
+
+
+def state_field(buffer: int, name: str, P: int, R: int, W: int, H: int):
+    off, eb, cnt = _SZ(), _SZ(), _SZ()
+    check(load().s3g_state_field(buffer, name.encode(), P, R, W, H, C.byref(off), C.byref(eb),
+                                 C.byref(cnt)), "s3g_state_field")
+    return off.value, eb.value, cnt.value

@@ -1,0 +1,333 @@
+// api.cu - extern "C" entry points of libs3g_b200.so (see include/s3g_b200.h).
+//
+// Host orchestration of the forward / backward passes; mirrors the control flow
+// of CudaRasterizer::Rasterizer::{markVisible,forward,backward}
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:141-153,198-339,343-444) behind a flat
+// C ABI.  No torch, no CPU fallback: every path ends in a kernel launch on the
+// caller's stream or in an error code.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/s3g_b200.h"
+#include "binning.cuh"
+#include "common.cuh"
+#include "composite.cuh"
+#include "preprocess.cuh"
+#include "radix_sort.cuh"
+
+using namespace s3g;
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_last_error = what;
+    if (e != cudaSuccess) {
+        g_last_error += ": ";
+        g_last_error += cudaGetErrorString(e);
+    }
+    return code;
+}
+
+#define S3G_CUDA(call, what)                                        \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return fail(S3G_ERR_CUDA, what, e__); \
+    } while (0)
+
+// debug mode: synchronise + check after every stage (CHECK_CUDA, auxiliary.h:166-173)
+#define S3G_STAGE(what)                                                            \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ == cudaSuccess && debug) e__ = cudaStreamSynchronize(stream);      \
+        if (e__ != cudaSuccess) return fail(S3G_ERR_CUDA, what, e__);              \
+    } while (0)
+
+// number of key bits that cover every tile id (getHigherMsb, rasterizer_impl.cu:35-50)
+int tile_key_bits(uint32_t tiles) {
+    int b = 0;
+    while (b < 32 && (tiles >> b) != 0) ++b;
+    return b < 1 ? 1 : b;
+}
+}  // namespace
+
+extern "C" {
+
+int s3g_abi_version(void) { return S3G_ABI_VERSION; }
+const char* s3g_last_error(void) { return g_last_error.c_str(); }
+const char* s3g_build_arch(void) { return "sm_100a"; }
+
+size_t s3g_geom_bytes(int64_t P) {
+    size_t t = 0;
+    GeomState::carve(nullptr, P, &t);
+    return t;
+}
+size_t s3g_binning_bytes(int64_t R) {
+    size_t t = 0;
+    BinningState::carve(nullptr, R, &t);
+    return t;
+}
+size_t s3g_image_bytes(int width, int height) {
+    size_t t = 0;
+    ImageState::carve(nullptr, width, height, &t);
+    return t;
+}
+size_t s3g_sort_temp_bytes(int64_t n) {
+    // look-back state + the two ping-pong arrays
+    size_t m = (size_t)(n > 0 ? n : 1);
+    return SortTemp::bytes(n) + 2 * (m * sizeof(uint32_t) + 128);
+}
+
+int s3g_state_field(int buffer, const char* name, int64_t P, int64_t R, int width, int height,
+                    size_t* offset, size_t* elem_bytes, size_t* count) {
+    if (!name || !offset || !elem_bytes || !count) return fail(S3G_ERR_ARG, "state_field: null argument");
+    // carve on a fake 128-aligned base so that pointers are offsets + base
+    char* base = reinterpret_cast<char*>((uintptr_t)1 << 40);
+    auto set = [&](const void* p, size_t eb, size_t n) {
+        *offset = (size_t)(reinterpret_cast<const char*>(p) - base);
+        *elem_bytes = eb;
+        *count = n;
+        return S3G_OK;
+    };
+    const std::string f(name);
+    if (buffer == 0) {
+        GeomState g = GeomState::carve(base, P);
+        if (f == "xyAB") return set(g.xyAB, 16, P);
+        if (f == "Cod") return set(g.Cod, 16, P);
+        if (f == "rgb") return set(g.rgb, 16, P);
+        if (f == "depth_key") return set(g.depth_key, 4, P);
+        if (f == "tiles_touched") return set(g.tiles_touched, 4, P);
+        if (f == "rect") return set(g.rect, 8, P);
+        if (f == "clamped") return set(g.clamped, 1, P);
+        if (f == "order") return set(g.order_a, 4, P);
+        if (f == "offsets") return set(g.offsets, 4, P);
+        if (f == "grad_rec") return set(g.grad_rec, 4, (size_t)P * GRAD_REC);
+    } else if (buffer == 1) {
+        BinningState b = BinningState::carve(base, R);
+        if (f == "point_list") return set(b.point_list, 4, R);
+        if (f == "point_list_tiles") return set(b.point_list_tiles, 4, R);
+    } else if (buffer == 2) {
+        ImageState s = ImageState::carve(base, width, height);
+        TileGrid tg = tile_grid(width, height);
+        if (f == "final_T") return set(s.final_T, 4, (size_t)width * height);
+        if (f == "n_contrib") return set(s.n_contrib, 4, (size_t)width * height);
+        if (f == "ranges") return set(s.ranges, 8, (size_t)tg.count());
+    }
+    return fail(S3G_ERR_ARG, "state_field: unknown buffer/field");
+}
+
+int s3g_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0) return fail(S3G_ERR_ARG, "mark_visible: P < 0");
+    if (P == 0) return S3G_OK;
+    if (!means3D || !viewmatrix || !projmatrix || !present)
+        return fail(S3G_ERR_ARG, "mark_visible: null pointer");
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, projmatrix,
+                                                             present);
+    S3G_CUDA(cudaGetLastError(), "mark_visible launch");
+    return S3G_OK;
+}
+
+int s3g_sort_pairs_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out,
+                       uint32_t* vals_out, int begin_bit, int end_bit, void* temp, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n < 0 || n >= (1ll << 30)) return fail(S3G_ERR_ARG, "sort: n out of range");
+    if (begin_bit < 0 || end_bit > 32 || end_bit <= begin_bit)
+        return fail(S3G_ERR_ARG, "sort: bad bit range");
+    if (n == 0) return S3G_OK;
+    // scratch ping-pong lives in temp after the SortTemp block
+    Carver c(static_cast<char*>(temp));
+    SortTemp st = SortTemp::carve(c, n);
+    uint32_t* kt = c.take<uint32_t>((size_t)n);
+    uint32_t* vt = c.take<uint32_t>((size_t)n);
+    S3G_CUDA(radix_sort_pairs((uint32_t)n, keys_in, vals_in, kt, vt, keys_out, vals_out, begin_bit,
+                              end_bit, st, stream),
+             "radix sort");
+    return S3G_OK;
+}
+
+int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binning_alloc,
+                              void* binning_user, s3g_alloc_fn image_alloc, void* image_user, int P,
+                              int D, int M, const float* background, int width, int height,
+                              const float* means3D, const float* shs, const float* colors_precomp,
+                              const float* opacities, const float* scales, float scale_modifier,
+                              const float* rotations, const float* cov3D_precomp,
+                              const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                              float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                              float* out_depth, int* radii, int debug, void* stream_) {
+    (void)prefiltered;   // the reference only uses it for a device-side trap (auxiliary.h:156-160)
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0 || width <= 0 || height <= 0) return fail(S3G_ERR_ARG, "forward: bad sizes");
+    if (!geom_alloc || !binning_alloc || !image_alloc) return fail(S3G_ERR_ARG, "forward: null allocator");
+    if (!out_color || !out_depth || !background) return fail(S3G_ERR_ARG, "forward: null output/background");
+    const size_t HW = (size_t)width * height;
+    if (P == 0) {   // rasterize_points.cu:82: outputs stay zero-filled
+        S3G_CUDA(cudaMemsetAsync(out_color, 0, 3 * HW * sizeof(float), stream), "memset color");
+        S3G_CUDA(cudaMemsetAsync(out_depth, 0, HW * sizeof(float), stream), "memset depth");
+        return 0;
+    }
+    if (!means3D || !opacities || !viewmatrix || !projmatrix)
+        return fail(S3G_ERR_ARG, "forward: null input");
+    if (!colors_precomp && !shs)
+        return fail(S3G_ERR_ARG, "forward: need SHs or precomputed colours");
+    if (!colors_precomp && !cam_pos) return fail(S3G_ERR_ARG, "forward: SH path needs cam_pos");
+    if (!cov3D_precomp && (!scales || !rotations))
+        return fail(S3G_ERR_ARG, "forward: need scales+rotations or precomputed cov3D");
+    if (!colors_precomp && (D < 0 || D > 3 || M < (D + 1) * (D + 1)))
+        return fail(S3G_ERR_ARG, "forward: SH degree/coefficient count mismatch");
+    if ((int64_t)P >= (1ll << 30)) return fail(S3G_ERR_ARG, "forward: P too large");
+
+    const TileGrid tg = tile_grid(width, height);
+    if (tg.x > 65535 || tg.y > 65535) return fail(S3G_ERR_ARG, "forward: image too large");
+
+    char* gptr = geom_alloc(geom_user, s3g_geom_bytes(P));
+    if (!gptr) return fail(S3G_ERR_ALLOC, "forward: geometry allocator returned NULL");
+    GeomState geom = GeomState::carve(gptr, P);
+    char* iptr = image_alloc(image_user, s3g_image_bytes(width, height));
+    if (!iptr) return fail(S3G_ERR_ALLOC, "forward: image allocator returned NULL");
+    ImageState img = ImageState::carve(iptr, width, height);
+    if (!radii) radii = geom.internal_radii;
+
+    // ---- per-Gaussian preprocess -----------------------------------------
+    PreFwdArgs pa;
+    pa.P = P; pa.D = D; pa.M = M;
+    pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier;
+    pa.rotations = rotations; pa.opacities = opacities; pa.shs = shs;
+    pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+    pa.view = viewmatrix; pa.proj = projmatrix; pa.campos = cam_pos;
+    pa.W = width; pa.H = height;
+    pa.tan_fovx = tan_fovx; pa.tan_fovy = tan_fovy;
+    pa.focal_y = height / (2.0f * tan_fovy);   // rasterizer_impl.cu:223-224
+    pa.focal_x = width / (2.0f * tan_fovx);
+    pa.radii = radii; pa.xyAB = geom.xyAB; pa.Cod = geom.Cod; pa.rgb = geom.rgb;
+    pa.depth_key = geom.depth_key; pa.tiles_touched = geom.tiles_touched; pa.rect = geom.rect;
+    pa.clamped = geom.clamped; pa.order = geom.order_a;
+    pa.grid_x = tg.x; pa.grid_y = tg.y;
+    preprocess_forward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pa);
+    S3G_STAGE("preprocess_forward");
+
+    // ---- depth digits of the LSD sort, over Gaussians --------------------
+    S3G_CUDA(radix_sort_pairs((uint32_t)P, geom.depth_key, geom.order_a, geom.key_b, geom.order_b,
+                              nullptr, geom.order_a, 0, 32, geom.sort, stream),
+             "depth sort");
+    S3G_STAGE("depth sort");
+
+    // ---- offsets in depth order + total ----------------------------------
+    {
+        const size_t zb = (size_t)(reinterpret_cast<char*>(geom.scan_misc + 32) -
+                                   reinterpret_cast<char*>(geom.scan_status));
+        S3G_CUDA(cudaMemsetAsync(geom.scan_status, 0, zb, stream), "memset scan");
+        const uint32_t nblk = (uint32_t)div_up64(P, SCAN_TILE);
+        scan_tiles_kernel<<<nblk, SCAN_THREADS, 0, stream>>>(geom.order_a, geom.tiles_touched,
+                                                             (uint32_t)P, geom.offsets,
+                                                             geom.scan_status, geom.scan_misc);
+        S3G_STAGE("scan");
+    }
+    uint64_t total = 0;   // rasterizer_impl.cu:281-282 (the one blocking read-back)
+    S3G_CUDA(cudaMemcpyAsync(&total, geom.scan_misc + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                             stream),
+             "num_rendered copy");
+    S3G_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
+    if (total >= (1ull << 30)) return fail(S3G_ERR_ARG, "forward: more than 2^30 tile instances");
+    const int64_t R = (int64_t)total;
+
+    char* bptr = binning_alloc(binning_user, s3g_binning_bytes(R));
+    if (!bptr) return fail(S3G_ERR_ALLOC, "forward: binning allocator returned NULL");
+    BinningState bin = BinningState::carve(bptr, R);
+
+    S3G_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)tg.count() * sizeof(uint2), stream),
+             "memset ranges");
+    if (R > 0) {
+        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+            (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, bin.tile_a,
+            bin.idx_a);
+        S3G_STAGE("emit");
+        S3G_CUDA(radix_sort_pairs((uint32_t)R, bin.tile_a, bin.idx_a, bin.tile_b, bin.idx_b,
+                                  bin.point_list_tiles, bin.point_list, 0,
+                                  tile_key_bits((uint32_t)tg.count()), bin.sort, stream),
+                 "tile sort");
+        S3G_STAGE("tile sort");
+        tile_ranges_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, stream>>>(
+            (uint32_t)R, bin.point_list_tiles, img.ranges);
+        S3G_STAGE("ranges");
+    }
+
+    RenderFwdArgs ra;
+    ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
+    ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb; ra.bg = background;
+    ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
+    ra.out_color = out_color; ra.out_depth = out_depth;
+    render_forward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+    S3G_STAGE("render_forward");
+    return R;
+}
+
+int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* background, int width,
+                           int height, const float* means3D, const float* shs,
+                           const float* colors_precomp, const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* campos,
+                           float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                           char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                           const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
+                           float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                           float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                           int debug, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(S3G_ERR_ARG, "backward: bad sizes");
+    if (P == 0) return S3G_OK;   // rasterize_points.cu:165
+    if (!geom_buffer || !image_buffer || (R > 0 && !binning_buffer))
+        return fail(S3G_ERR_STATE, "backward: missing state buffer");
+    if (!means3D || !viewmatrix || !projmatrix || !background || !dL_dpix || !dL_dpix_depth)
+        return fail(S3G_ERR_ARG, "backward: null input");
+    if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
+        !dL_drot)
+        return fail(S3G_ERR_ARG, "backward: null gradient output");
+    const bool use_sh = (colors_precomp == nullptr);
+    if (use_sh && (!shs || !dL_dsh || !campos)) return fail(S3G_ERR_ARG, "backward: SH path needs shs, dL_dsh, campos");
+    if (!cov3D_precomp && (!scales || !rotations))
+        return fail(S3G_ERR_ARG, "backward: need scales+rotations or precomputed cov3D");
+
+    GeomState geom = GeomState::carve(geom_buffer, P);
+    BinningState bin = BinningState::carve(binning_buffer, R);
+    ImageState img = ImageState::carve(image_buffer, width, height);
+    if (!radii) radii = geom.internal_radii;
+    const TileGrid tg = tile_grid(width, height);
+
+    S3G_CUDA(cudaMemsetAsync(geom.grad_rec, 0, (size_t)P * GRAD_REC * sizeof(float), stream),
+             "memset grad_rec");
+    if (R > 0) {
+        RenderBwdArgs ra;
+        ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
+        ra.bg = background; ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb;
+        ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
+        ra.dL_dpix = dL_dpix; ra.dL_dpix_depth = dL_dpix_depth; ra.grad_rec = geom.grad_rec;
+        render_backward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+        S3G_STAGE("render_backward");
+    }
+
+    PreBwdArgs pb;
+    pb.P = P; pb.D = D; pb.M = use_sh ? M : 0;
+    pb.means3D = means3D; pb.radii = radii;
+    pb.shs = use_sh ? shs : nullptr;   // backward.cu:406
+    pb.clamped = geom.clamped;
+    pb.scales = cov3D_precomp ? nullptr : scales;   // backward.cu:410 (the reference keys on scales)
+    pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+    pb.cov3D_precomp = cov3D_precomp;
+    pb.view = viewmatrix; pb.proj = projmatrix; pb.campos = campos;
+    pb.focal_y = height / (2.0f * tan_fovy);
+    pb.focal_x = width / (2.0f * tan_fovx);
+    pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy;
+    pb.grad_rec = geom.grad_rec;
+    pb.dL_dmean2D = dL_dmean2D; pb.dL_dconic = dL_dconic; pb.dL_dopacity = dL_dopacity;
+    pb.dL_dcolor = dL_dcolor; pb.dL_ddepth = dL_ddepth; pb.dL_dmean3D = dL_dmean3D;
+    pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = use_sh ? dL_dsh : nullptr;
+    pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot;
+    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pb);
+    S3G_STAGE("preprocess_backward");
+    return S3G_OK;
+}
+
+}  // extern "C"

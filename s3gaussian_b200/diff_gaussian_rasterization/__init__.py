@@ -1,0 +1,264 @@
+"""Drop-in for the reference's ``diff_gaussian_rasterization`` module.
+
+Same public surface as DGR/diff_gaussian_rasterization/__init__.py
+(``GaussianRasterizationSettings`` :158-170, ``GaussianRasterizer`` :172-221,
+``rasterize_gaussians`` :21-42), same argument meaning and error behaviour, but
+the work is done by libs3g_b200.so through its C ABI (include/s3g_b200.h):
+torch only owns the tensors and the stream.
+
+    from s3gaussian_b200.diff_gaussian_rasterization import (
+        GaussianRasterizationSettings, GaussianRasterizer)
+
+`s3gaussian_b200.install_as_reference_module()` registers this module under the
+name ``diff_gaussian_rasterization`` so the reference's
+``gaussian_renderer/__init__.py:18`` import resolves to it unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item
+                      for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+class _Arena:
+    """A growable device byte buffer handed to the C side as an s3g_alloc_fn
+    (what resizeFunctional() does with a torch tensor, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:   # pragma: no cover - surfaced as S3G_ERR_ALLOC
+            return 0
+
+
+def _ptr(t: torch.Tensor | None):
+    """device pointer, or NULL for the reference's 'absent' empty tensors
+    (torch.Tensor([]), DGR/.../__init__.py:198-208)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 tensor, got {t.dtype}")
+    if t.device != device:
+        raise RuntimeError(f"tensor on {t.device}, expected {device}")
+    return t.contiguous()   # rasterize_points.cu:95-113
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        lib = _lib.load()
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+        if not means3D.is_cuda:
+            raise RuntimeError("s3gaussian_b200 has no CPU path: means3D must be a CUDA tensor")
+        dev = means3D.device
+        rs = raster_settings
+        P = means3D.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+
+        means3D = _f32c(means3D, dev)
+        sh = _f32c(sh, dev)
+        colors_precomp = _f32c(colors_precomp, dev)
+        opacities = _f32c(opacities, dev)
+        scales = _f32c(scales, dev)
+        rotations = _f32c(rotations, dev)
+        cov3Ds_precomp = _f32c(cov3Ds_precomp, dev)
+        bg = _f32c(rs.bg, dev)
+        view = _f32c(rs.viewmatrix, dev)
+        proj = _f32c(rs.projmatrix, dev)
+        campos = _f32c(rs.campos, dev)
+
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+        M = sh.size(1) if sh.numel() != 0 else 0
+
+        args = (geom.cb, None, binning.cb, None, img.cb, None, P, int(rs.sh_degree), M, _ptr(bg), W, H,
+                _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
+                float(rs.scale_modifier), _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(view),
+                _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
+                int(bool(rs.prefiltered)), color.data_ptr(), depth.data_ptr(), _ptr(radii),
+                int(bool(rs.debug)), _stream_ptr(dev))
+        with torch.cuda.device(dev):
+            if rs.debug:
+                cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, colors_precomp, opacities, scales,
+                                                rotations, rs.scale_modifier, cov3Ds_precomp,
+                                                rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
+                                                rs.image_height, rs.image_width, sh, rs.sh_degree,
+                                                rs.campos, rs.prefiltered, rs.debug))
+                try:
+                    num_rendered = _lib.check(lib.s3g_rasterize_forward(*args), "rasterize_gaussians")
+                except Exception as ex:
+                    torch.save(cpu_args, "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                    raise ex
+            else:
+                num_rendered = _lib.check(lib.s3g_rasterize_forward(*args), "rasterize_gaussians")
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = int(num_rendered)
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
+                              geom.tensor, binning.tensor, img.tensor)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        lib = _lib.load()
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+         binningBuffer, imgBuffer) = ctx.saved_tensors
+        dev = means3D.device
+        P = means3D.size(0)
+        H, W = int(rs.image_height), int(rs.image_width)
+        M = sh.size(1) if sh.numel() != 0 else 0
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        if grad_depth is None:
+            grad_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
+        grad_out_color = _f32c(grad_out_color, dev)
+        grad_depth = _f32c(grad_depth, dev)
+        bg = _f32c(rs.bg, dev)
+        view = _f32c(rs.viewmatrix, dev)
+        proj = _f32c(rs.projmatrix, dev)
+        campos = _f32c(rs.campos, dev)
+
+        def e(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        # every element is written by the kernel (zeros where radii <= 0): no memsets
+        grad_means3D, grad_means2D = e(P, 3), e(P, 3)
+        grad_colors, grad_opacities = e(P, 3), e(P, 1)
+        grad_cov3D, grad_sh = e(P, 6), e(P, M, 3)
+        grad_scales, grad_rotations = e(P, 3), e(P, 4)
+
+        args = (P, int(rs.sh_degree), M, ctx.num_rendered, _ptr(bg), W, H, _ptr(means3D), _ptr(sh),
+                _ptr(colors_precomp), _ptr(scales), float(rs.scale_modifier), _ptr(rotations),
+                _ptr(cov3Ds_precomp), _ptr(view), _ptr(proj), _ptr(campos), float(rs.tanfovx),
+                float(rs.tanfovy), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
+                _ptr(imgBuffer), grad_out_color.data_ptr(), grad_depth.data_ptr(),
+                _ptr(grad_means2D), None, _ptr(grad_opacities), _ptr(grad_colors), None,
+                _ptr(grad_means3D), _ptr(grad_cov3D), _ptr(grad_sh), _ptr(grad_scales),
+                _ptr(grad_rotations), int(bool(rs.debug)), _stream_ptr(dev))
+        with torch.cuda.device(dev):
+            if P > 0:
+                if rs.debug:
+                    try:
+                        _lib.check(lib.s3g_rasterize_backward(*args), "rasterize_gaussians_backward")
+                    except Exception as ex:
+                        print("\nAn error occured in backward.\n")
+                        raise ex
+                else:
+                    _lib.check(lib.s3g_rasterize_backward(*args), "rasterize_gaussians_backward")
+
+        has_colors = colors_precomp.numel() != 0
+        has_cov = cov3Ds_precomp.numel() != 0
+        grads = (
+            grad_means3D,
+            grad_means2D,
+            grad_sh if not has_colors else None,
+            grad_colors if has_colors else None,
+            grad_opacities,
+            grad_scales if not has_cov else None,
+            grad_rotations if not has_cov else None,
+            grad_cov3D if has_cov else None,
+            None,
+        )
+        return grads
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """bool[P]: passes the near-plane test (rasterizer_impl.cu:54-66)."""
+        lib = _lib.load()
+        with torch.no_grad():
+            rs = self.raster_settings
+            dev = positions.device
+            if not positions.is_cuda:
+                raise RuntimeError("s3gaussian_b200 has no CPU path: positions must be a CUDA tensor")
+            positions = _f32c(positions, dev)
+            P = positions.size(0)
+            present = torch.zeros((P,), dtype=torch.bool, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.s3g_mark_visible(P, _ptr(positions), _ptr(_f32c(rs.viewmatrix, dev)),
+                                                _ptr(_f32c(rs.projmatrix, dev)), _ptr(present),
+                                                _stream_ptr(dev)), "mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, raster_settings)

@@ -1,0 +1,77 @@
+"""Loader + state decoder for the REAL reference extension (oracle/_ref), test-only.
+
+oracle/_ref/diff_gaussian_rasterization is the unmodified reference CUDA
+rasterizer built for sm_100 by oracle/build_ref.sh; it travels to the GPU box
+as a prebuilt artefact.  The decoders below re-derive the byte layout of its
+three opaque buffers (DGR/cuda_rasterizer/rasterizer_impl.cu:155-194,
+rasterizer_impl.h:22-31: each field is 128-byte aligned, in declaration order)
+so tests can compare internal state bit for bit.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+_mod = None
+
+
+def available() -> bool:
+    d = os.path.join(REF_DIR, "diff_gaussian_rasterization")
+    return os.path.isdir(d) and any(f.startswith("_C") and f.endswith(".so") for f in os.listdir(d))
+
+
+def load():
+    """import the reference module under the name ``ref_diff_gaussian_rasterization``"""
+    global _mod
+    if _mod is None:
+        if not available():
+            raise RuntimeError("oracle/_ref is not built (run oracle/build_ref.sh where /root/reference exists)")
+        spec = importlib.util.spec_from_file_location(
+            "ref_diff_gaussian_rasterization",
+            os.path.join(REF_DIR, "diff_gaussian_rasterization", "__init__.py"),
+            submodule_search_locations=[os.path.join(REF_DIR, "diff_gaussian_rasterization")])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["ref_diff_gaussian_rasterization"] = mod
+        spec.loader.exec_module(mod)
+        _mod = mod
+    return _mod
+
+
+def _carve(buf: torch.Tensor, fields):
+    """fields: list of (name, np dtype, count). Returns dict of numpy arrays."""
+    raw = buf.detach().cpu().numpy()
+    base = buf.data_ptr()
+    off = 0
+    out = {}
+    for name, dt, count in fields:
+        a = ((base + off + 127) & ~127) - base
+        nbytes = np.dtype(dt).itemsize * count
+        if name is not None:
+            out[name] = raw[a:a + nbytes].view(dt).copy()
+        off = a + nbytes
+    return out
+
+
+def decode_geom(buf, P):
+    return _carve(buf, [("depths", np.float32, P), ("clamped", np.uint8, 3 * P),
+                        ("internal_radii", np.int32, P), ("means2D", np.float32, 2 * P),
+                        ("cov3D", np.float32, 6 * P), ("conic_opacity", np.float32, 4 * P),
+                        ("rgb", np.float32, 3 * P), ("tiles_touched", np.uint32, P)])
+
+
+def decode_binning(buf, R):
+    return _carve(buf, [("point_list", np.uint32, R), ("point_list_unsorted", np.uint32, R),
+                        ("point_list_keys", np.uint64, R)])
+
+
+def decode_image(buf, N):
+    return _carve(buf, [("accum_alpha", np.float32, N), ("n_contrib", np.uint32, N),
+                        ("ranges", np.uint32, 2 * N)])

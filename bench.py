@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py - the hot path of BASELINE.json on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the unmodified reference extension (oracle/_ref)
+
+Metric (BASELINE.json): fwd+bwd Gaussians/s at 2M points, 1920x1280.
+A "step" is one pass of the render hot path over one view: rasterizer forward
+(preprocess, depth/tile sort, composite) + backward (composite, preprocess) for
+P Gaussians through the drop-in GaussianRasterizer API, i.e. through the C ABI of
+libs3g_b200.so.  At N > 1 every rank renders its own view of the same replicated
+cloud (one camera per GPU) and the per-Gaussian gradients are
+all-reduced over NCCL inside the step; `value` = N * P / step time (weak scaling).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, CUDA-event
+timed, max over ranks.  `e2e`: the same step driven from HOST buffers - camera
+matrices and the ground-truth image/depth come from pinned host memory every step,
+loss = L1(rgb) + 0.5*L2(depth) is computed on the device and read back.
+`roofline`: the dominant kernel (backward composite) timed with CUDA events on its
+launching stream inside the library (s3g_profile_*), algorithmic bytes from
+SURVEY.md 8d.  `cpu_baseline`: the CPU oracle on a bounded sample of the same
+workload on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=2_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1280)
+    ap.add_argument("--mode", default="sh", choices=["sh", "rgb"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=500_000)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "500"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def load_impl(name):
+    if name == "ours":
+        from s3gaussian_b200 import build
+        build.build()
+        from s3gaussian_b200 import diff_gaussian_rasterization as m
+        return m
+    import ref_ext
+    if not ref_ext.available():
+        return None
+    return ref_ext.load()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    mod = load_impl(a.impl)
+    if mod is None:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    from s3gaussian_b200 import synthetic as syn
+    import util
+
+    P, W, H = a.points, a.width, a.height
+    cloud = syn.make_cloud(P, seed=0)
+    ring = syn.waymo_ring(W, H, frames=50)
+    cam = ring[1 + 3 * ((rank * 6) % 50)]          # front camera of frame 6*rank
+    d = util.scene_inputs(cloud, cam, mode=a.mode, sh_degree=3, bg=(0.0, 0.0, 0.0))
+    t = {k: (d[k].to(dev).requires_grad_(True) if d[k] is not None else None) for k in util.TENSOR_KEYS}
+    m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    gc = torch.randn(3, H, W, device=dev, generator=g)
+    gd = torch.randn(1, H, W, device=dev, generator=g)
+    leaves = [v for v in list(t.values()) + [m2d] if v is not None]
+    settings = util.settings_for(mod, d, dev)
+    rast = mod.GaussianRasterizer(settings)
+
+    def zero_grads():
+        for v in leaves:
+            v.grad = None
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([v.grad.reshape(-1) for v in leaves if v is not m2d])
+            dist.all_reduce(flat)
+            return flat
+        return None
+
+    def step_resident():
+        zero_grads()
+        color, radii, depth = rast(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"],
+                                   colors_precomp=t["colors_precomp"], scales=t["scales"],
+                                   rotations=t["rotations"], cov3D_precomp=None)
+        torch.autograd.backward([color, depth], [gc, gd])
+        allreduce_grads()
+        return radii
+
+    # ---- host-driven end-to-end step -------------------------------------
+    gt_img = torch.rand(3, H, W).pin_memory()
+    gt_dep = (torch.rand(1, H, W) * 50).pin_memory()
+    cam_host = torch.cat([d["viewmatrix"].reshape(-1), d["projmatrix"].reshape(-1), d["campos"].reshape(-1)]).pin_memory()
+    h2d_bytes = gt_img.numel() * 4 + gt_dep.numel() * 4 + cam_host.numel() * 4
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e():
+        zero_grads()
+        cam_d = cam_host.to(dev, non_blocking=True)
+        img_d = gt_img.to(dev, non_blocking=True)
+        dep_d = gt_dep.to(dev, non_blocking=True)
+        rs = settings._replace(viewmatrix=cam_d[:16].view(4, 4), projmatrix=cam_d[16:32].view(4, 4), campos=cam_d[32:35])
+        r = mod.GaussianRasterizer(rs)
+        color, radii, depth = r(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"],
+                                colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"],
+                                cov3D_precomp=None)
+        loss = (color - img_d).abs().mean() + 0.5 * ((depth - dep_d) ** 2).mean()
+        loss.backward()
+        allreduce_grads()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()          # the reference launches on the legacy stream: device-wide sync
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(tt[0])
+        return ms
+
+    if a.impl == "ours":
+        from s3gaussian_b200 import _lib
+        _lib.profile_enable(True)
+    sampler = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
+    if sampler:
+        sampler.start()
+    ms_res = timed(step_resident, a.steps, max(a.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, a.steps, 3)
+
+    radii = step_resident()
+    torch.cuda.synchronize()
+    V = int((radii > 0).sum())
+
+    # ---- roofline of the dominant kernel ----------------------------------
+    roofline, stages = None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    R = None
+    if a.impl == "ours":
+        from s3gaussian_b200 import _lib
+        acc_f, acc_b, n = {}, {}, 5
+        for _ in range(n):
+            step_resident()
+            torch.cuda.synchronize()
+            for k, v in _lib.profile_read(0).items():
+                acc_f[k] = acc_f.get(k, 0.0) + v / n
+            for k, v in _lib.profile_read(1).items():
+                acc_b[k] = acc_b.get(k, 0.0) + v / n
+        _lib.profile_enable(False)
+        stages = {"forward_ms": {k: round(v, 4) for k, v in acc_f.items()},
+                  "backward_ms": {k: round(v, 4) for k, v in acc_b.items()}}
+        color, radii2, depth2, R, _views = util.ours_forward_state(d, dev)
+        kern_ms = acc_b.get("render_backward", 0.0)
+        # SURVEY.md 8d, backward composite: per instance id 4 + record 40, per pixel 24,
+        # per visible Gaussian the 40-byte gradient record it produces
+        alg = R * 44 + W * H * 24 + V * 40
+        ach = alg / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        roofline = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": round(ach, 2), "peak": hbm,
+                    "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+                    "algorithmic_bytes": int(alg), "kernel_ms": round(kern_ms, 4), "peak_source": peak_src,
+                    "note": "issue-bound all-lanes composite; see DESIGN.md (roofline) for why the HBM fraction is low"}
+        sh = a.mode == "sh"
+        step_bytes = (P * (480 if sh else 120) + V * (356 if sh else 176) + R * 132 + W * H * 48)
+        step_ms = ms_res / a.steps
+        roofline["step"] = {"algorithmic_bytes": int(step_bytes), "achieved": round(step_bytes / (step_ms * 1e-3) / 1e9, 2),
+                            "frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / hbm, 4)}
+
+    # ---- CPU baseline (rank 0, N == 1) -------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.impl == "ours":
+        import dataclasses
+        from oracle import splat_oracle
+        splat_oracle.build()
+        n = min(a.cpu_sample, P)
+        sub = syn.GaussianCloud(*(getattr(cloud, f.name)[:n] for f in dataclasses.fields(cloud)))
+        ds = util.scene_inputs(sub, cam, mode=a.mode, sh_degree=3, bg=(0.0, 0.0, 0.0))
+        t0 = time.time()
+        util.oracle_run(splat_oracle, ds, gc.cpu(), gd.cpu())
+        dt = time.time() - t0
+        cpu = {"value": round(n / dt, 1), "unit": "Gaussians/s", "cores": 1, "kind": "port",
+               "sample": f"first {n} Gaussians of the workload cloud, same camera and resolution, fwd+bwd, "
+                         f"oracle/splat_oracle.c single thread, {dt:.1f} s; host has {os.cpu_count()} cores"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    step_ms = ms_res / a.steps
+    value = world * P / (step_ms * 1e-3)
+    e2e_ms = ms_e2e / a.steps
+    out = {
+        "metric": "fwd+bwd Gaussians/s (rasterizer forward+backward, one view per GPU)",
+        "value": round(value, 1), "unit": "Gaussians/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{P} Gaussians ({'SH deg 3 in-kernel' if a.mode == 'sh' else 'precomputed colours'}), "
+                               f"{W}x{H}, 1 view/GPU of the 50-frame ring, rasterizer fwd+bwd"
+                               + (", NCCL all-reduce of per-Gaussian grads" if world > 1 else ""),
+                   "points": P, "width": W, "height": H, "visible": V, "num_rendered": R,
+                   "parallelism": f"view-parallel dp{world}",
+                   "l2": "inputs (>= 470 MB of Gaussian parameters + sort arenas) exceed the 126 MB L2; no flush needed"},
+        "e2e": {"value": round(world * P / (e2e_ms * 1e-3), 1), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4),
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                "what": "camera + GT image/depth H2D from pinned memory, render through the GaussianRasterizer API, "
+                        "L1+depth-L2 loss, backward, loss D2H"},
+        "gpu_launches": (16 * a.steps) if a.impl == "ours" else 0,
+        "clocks": clocks,
+    }
+    if a.impl == "reference":
+        out["impl"] = "reference"
+        out["gpu_launches"] = 0
+        out["cpu_baseline"] = {"value": out["value"], "unit": "Gaussians/s", "cores": 1, "kind": "reference",
+                               "sample": "full workload; the reference's implementation of this path is its CUDA "
+                                         "extension (oracle/_ref, unmodified, sm_100), timed on the same B200 as "
+                                         "north_star asks - there is no CPU implementation of the rasterizer upstream"}
+    else:
+        out["roofline"] = roofline
+        out["stages"] = stages
+        if cpu:
+            out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

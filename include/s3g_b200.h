@@ -156,6 +156,16 @@ size_t s3g_geom_bytes(int64_t P);
 size_t s3g_binning_bytes(int64_t R);
 size_t s3g_image_bytes(int width, int height);
 
+/* ---- per-stage device timing (bench.py roofline leg) ----------------------
+ * When enabled, forward/backward bracket every kernel stage with cudaEvents on
+ * the caller's stream.  s3g_profile_read() synchronises those events and copies
+ * the last call's stage times (milliseconds) into `ms`; returns the number of
+ * stages written (names via s3g_profile_stage_name).  `which`: 0 = forward,
+ * 1 = backward. */
+int s3g_profile_enable(int on);
+int s3g_profile_read(int which, float* ms, int capacity);
+const char* s3g_profile_stage_name(int which, int index);
+
 /* ---- standalone device radix sort (exposed for tests) -------------------
  * Stable LSD sort of n (key,value) u32 pairs on key bits [begin_bit,end_bit).
  * keys_out/vals_out receive the result; keys_in/vals_in are clobbered; `temp`

@@ -33,6 +33,9 @@ SIGNATURES = {
                                     _V, _V, _V, _I, _V]),
     "s3g_state_field": (_I, [_I, C.c_char_p, _I64, _I64, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ),
                              C.POINTER(_SZ)]),
+    "s3g_profile_enable": (_I, [_I]),
+    "s3g_profile_read": (_I, [_I, _V, _I]),
+    "s3g_profile_stage_name": (C.c_char_p, [_I, _I]),
     "s3g_geom_bytes": (_SZ, [_I64]),
     "s3g_binning_bytes": (_SZ, [_I64]),
     "s3g_image_bytes": (_SZ, [_I, _I]),
@@ -77,3 +80,15 @@ def state_field(buffer: int, name: str, P: int, R: int, W: int, H: int):
     check(load().s3g_state_field(buffer, name.encode(), P, R, W, H, C.byref(off), C.byref(eb),
                                  C.byref(cnt)), "s3g_state_field")
     return off.value, eb.value, cnt.value
+
+
+def profile_enable(on: bool) -> None:
+    load().s3g_profile_enable(1 if on else 0)
+
+
+def profile_read(which: int) -> dict:
+    """{stage name: milliseconds} of the last forward (0) / backward (1) call."""
+    lib = load()
+    buf = (C.c_float * 16)()
+    n = check(lib.s3g_profile_read(which, buf, 16), "s3g_profile_read")
+    return {lib.s3g_profile_stage_name(which, i).decode(): float(buf[i]) for i in range(n)}

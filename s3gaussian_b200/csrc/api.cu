@@ -44,6 +44,27 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         if (e__ != cudaSuccess) return fail(S3G_ERR_CUDA, what, e__);              \
     } while (0)
 
+// ---- optional per-stage timing -------------------------------------------
+constexpr int kMaxStages = 12;
+struct StageTimer {
+    bool on = false;
+    int n[2] = {0, 0};
+    cudaEvent_t ev[2][kMaxStages + 1] = {};
+    const char* names[2][kMaxStages] = {};
+    void mark(int which, cudaStream_t s, const char* name_of_stage_that_starts) {
+        if (!on) return;
+        int i = n[which];
+        if (i > kMaxStages) return;
+        if (!ev[which][i]) cudaEventCreate(&ev[which][i]);
+        cudaEventRecord(ev[which][i], s);
+        if (name_of_stage_that_starts && i < kMaxStages) names[which][i] = name_of_stage_that_starts;
+        n[which] = i + 1;
+    }
+    void begin(int which) { n[which] = 0; }
+};
+StageTimer g_timer;
+#define S3G_MARK(which, name) g_timer.mark(which, stream, name)
+
 // number of key bits that cover every tile id (getHigherMsb, rasterizer_impl.cu:35-50)
 int tile_key_bits(uint32_t tiles) {
     int b = 0;
@@ -57,6 +78,27 @@ extern "C" {
 int s3g_abi_version(void) { return S3G_ABI_VERSION; }
 const char* s3g_last_error(void) { return g_last_error.c_str(); }
 const char* s3g_build_arch(void) { return "sm_100a"; }
+
+int s3g_profile_enable(int on) {
+    g_timer.on = on != 0;
+    return S3G_OK;
+}
+int s3g_profile_read(int which, float* ms, int capacity) {
+    if (which < 0 || which > 1 || !ms) return fail(S3G_ERR_ARG, "profile_read: bad argument");
+    int stages = g_timer.n[which] - 1;
+    if (stages < 0) stages = 0;
+    if (stages > capacity) stages = capacity;
+    for (int i = 0; i < stages; ++i) {
+        cudaError_t e = cudaEventSynchronize(g_timer.ev[which][i + 1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[i], g_timer.ev[which][i], g_timer.ev[which][i + 1]);
+        if (e != cudaSuccess) return fail(S3G_ERR_CUDA, "profile_read", e);
+    }
+    return stages;
+}
+const char* s3g_profile_stage_name(int which, int index) {
+    if (which < 0 || which > 1 || index < 0 || index >= kMaxStages || !g_timer.names[which][index]) return "";
+    return g_timer.names[which][index];
+}
 
 size_t s3g_geom_bytes(int64_t P) {
     size_t t = 0;
@@ -205,8 +247,25 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     pa.depth_key = geom.depth_key; pa.tiles_touched = geom.tiles_touched; pa.rect = geom.rect;
     pa.clamped = geom.clamped; pa.order = geom.order_a;
     pa.grid_x = tg.x; pa.grid_y = tg.y;
-    preprocess_forward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pa);
+    g_timer.begin(0);
+    S3G_MARK(0, "preprocess_forward");
+    {
+        const bool use_sh = colors_precomp == nullptr;
+        const size_t smem = use_sh ? (size_t)(PRE_THREADS / 32) * 32 * row_stride(3 * M) * sizeof(float) : 0;
+        if (smem > 200 * 1024) return fail(S3G_ERR_ARG, "forward: too many SH coefficients");
+        const int grid = (P + PRE_THREADS - 1) / PRE_THREADS;
+        if (use_sh && M == 16) {
+            preprocess_forward_kernel<16><<<grid, PRE_THREADS, smem, stream>>>(pa);
+        } else {
+            if (smem > 48 * 1024)
+                S3G_CUDA(cudaFuncSetAttribute(preprocess_forward_kernel<0>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "smem attribute");
+            preprocess_forward_kernel<0><<<grid, PRE_THREADS, smem, stream>>>(pa);
+        }
+    }
     S3G_STAGE("preprocess_forward");
+    S3G_MARK(0, "depth_sort");
 
     // ---- depth digits of the LSD sort, over Gaussians --------------------
     S3G_CUDA(radix_sort_pairs((uint32_t)P, geom.depth_key, geom.order_a, geom.key_b, geom.order_b,
@@ -214,6 +273,7 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
              "depth sort");
     S3G_STAGE("depth sort");
 
+    S3G_MARK(0, "scan+readback");
     // ---- offsets in depth order + total ----------------------------------
     {
         const size_t zb = (size_t)(reinterpret_cast<char*>(geom.scan_misc + 32) -
@@ -225,11 +285,30 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
                                                              geom.scan_status, geom.scan_misc);
         S3G_STAGE("scan");
     }
-    uint64_t total = 0;   // rasterizer_impl.cu:281-282 (the one blocking read-back)
-    S3G_CUDA(cudaMemcpyAsync(&total, geom.scan_misc + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                             stream),
-             "num_rendered copy");
-    S3G_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
+    // rasterizer_impl.cu:281-282: the one read-back that sizes the binning arena.  Pinned
+    // destination + event spin-wait: a blocking cudaStreamSynchronize() after a long queue
+    // sleeps in the OS and wakes up milliseconds late, which idles the GPU.
+    uint64_t total = 0;
+    {
+        static thread_local uint64_t* h_total = nullptr;
+        static thread_local cudaEvent_t ev = nullptr;
+        if (!h_total) {
+            S3G_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total), sizeof(uint64_t), cudaHostAllocDefault),
+                     "pinned readback alloc");
+            S3G_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "readback event");
+        }
+        S3G_CUDA(cudaMemcpyAsync(h_total, geom.scan_misc + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream),
+                 "num_rendered copy");
+        S3G_CUDA(cudaEventRecord(ev, stream), "num_rendered event");
+        cudaError_t q;
+        while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (q != cudaSuccess) return fail(S3G_ERR_CUDA, "num_rendered wait", q);
+        total = *h_total;
+    }
     if (total >= (1ull << 30)) return fail(S3G_ERR_ARG, "forward: more than 2^30 tile instances");
     const int64_t R = (int64_t)total;
 
@@ -239,21 +318,25 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
 
     S3G_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)tg.count() * sizeof(uint2), stream),
              "memset ranges");
+    S3G_MARK(0, "emit");
     if (R > 0) {
         emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
             (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, bin.tile_a,
             bin.idx_a);
         S3G_STAGE("emit");
+        S3G_MARK(0, "tile_sort");
         S3G_CUDA(radix_sort_pairs((uint32_t)R, bin.tile_a, bin.idx_a, bin.tile_b, bin.idx_b,
                                   bin.point_list_tiles, bin.point_list, 0,
                                   tile_key_bits((uint32_t)tg.count()), bin.sort, stream),
                  "tile sort");
         S3G_STAGE("tile sort");
+        S3G_MARK(0, "tile_ranges");
         tile_ranges_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, stream>>>(
             (uint32_t)R, bin.point_list_tiles, img.ranges);
         S3G_STAGE("ranges");
     }
 
+    S3G_MARK(0, "render_forward");
     RenderFwdArgs ra;
     ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
     ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb; ra.bg = background;
@@ -261,6 +344,7 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     ra.out_color = out_color; ra.out_depth = out_depth;
     render_forward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
     S3G_STAGE("render_forward");
+    S3G_MARK(0, nullptr);
     return R;
 }
 
@@ -296,8 +380,11 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     if (!radii) radii = geom.internal_radii;
     const TileGrid tg = tile_grid(width, height);
 
+    g_timer.begin(1);
+    S3G_MARK(1, "zero_grad_rec");
     S3G_CUDA(cudaMemsetAsync(geom.grad_rec, 0, (size_t)P * GRAD_REC * sizeof(float), stream),
              "memset grad_rec");
+    S3G_MARK(1, "render_backward");
     if (R > 0) {
         RenderBwdArgs ra;
         ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
@@ -308,6 +395,7 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
         S3G_STAGE("render_backward");
     }
 
+    S3G_MARK(1, "preprocess_backward");
     PreBwdArgs pb;
     pb.P = P; pb.D = D; pb.M = use_sh ? M : 0;
     pb.means3D = means3D; pb.radii = radii;
@@ -325,8 +413,22 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     pb.dL_dcolor = dL_dcolor; pb.dL_ddepth = dL_ddepth; pb.dL_dmean3D = dL_dmean3D;
     pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = use_sh ? dL_dsh : nullptr;
     pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot;
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(pb);
+    {
+        const size_t smem = use_sh ? (size_t)(PRE_THREADS / 32) * 32 * row_stride(3 * M) * sizeof(float) : 0;
+        if (smem > 200 * 1024) return fail(S3G_ERR_ARG, "backward: too many SH coefficients");
+        const int grid = (P + PRE_THREADS - 1) / PRE_THREADS;
+        if (use_sh && M == 16) {
+            preprocess_backward_kernel<16><<<grid, PRE_THREADS, smem, stream>>>(pb);
+        } else {
+            if (smem > 48 * 1024)
+                S3G_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<0>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "smem attribute");
+            preprocess_backward_kernel<0><<<grid, PRE_THREADS, smem, stream>>>(pb);
+        }
+    }
     S3G_STAGE("preprocess_backward");
+    S3G_MARK(1, nullptr);
     return S3G_OK;
 }
 

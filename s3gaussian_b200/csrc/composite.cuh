@@ -69,10 +69,17 @@ struct RenderFwdArgs {
     float* out_depth;
 };
 
+// One staged instance: 48 bytes = three 16-byte gathers.  Lane j of the cull
+// test reads element j: LDS.128 at a 12-word stride is conflict-free per
+// quarter-warp.
+struct __align__(16) Rec {
+    float4 a;   // pix.x, pix.y, conic.x, conic.y
+    float4 b;   // conic.z, opacity, depth, tau_cull
+    float4 c;   // r, g, b, -
+};
+
 __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs a) {
-    __shared__ __align__(16) float4 s_xyAB[2][CB];
-    __shared__ __align__(16) float4 s_Cod[2][CB];
-    __shared__ __align__(16) float4 s_rgb[2][CB];
+    __shared__ Rec s_rec[2][CB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -93,15 +100,15 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
     float T = 1.0f;
     uint32_t last_contributor = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    bool done = !inside;
+    bool alive = inside;
 
     // prologue: gather batch 0, fetch the id of batch 1
     uint32_t id_next = 0;
     if (tid < n) {
         const uint32_t id = a.point_list[range.x + tid];
-        cp_async16(&s_xyAB[0][tid], &a.xyAB[id]);
-        cp_async16(&s_Cod[0][tid], &a.Cod[id]);
-        cp_async16(&s_rgb[0][tid], &a.rgb[id]);
+        cp_async16(&s_rec[0][tid].a, &a.xyAB[id]);
+        cp_async16(&s_rec[0][tid].b, &a.Cod[id]);
+        cp_async16(&s_rec[0][tid].c, &a.rgb[id]);
     }
     cp_async_commit();
     if (CB + tid < n) id_next = a.point_list[range.x + CB + tid];
@@ -112,56 +119,56 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
         const int buf = b & 1;
         // prefetch batch b+1 into the other buffer, and the ids of batch b+2
         if ((b + 1) * CB + tid < n) {
-            cp_async16(&s_xyAB[buf ^ 1][tid], &a.xyAB[id_next]);
-            cp_async16(&s_Cod[buf ^ 1][tid], &a.Cod[id_next]);
-            cp_async16(&s_rgb[buf ^ 1][tid], &a.rgb[id_next]);
+            cp_async16(&s_rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
+            cp_async16(&s_rec[buf ^ 1][tid].b, &a.Cod[id_next]);
+            cp_async16(&s_rec[buf ^ 1][tid].c, &a.rgb[id_next]);
         }
         cp_async_commit();
         if ((b + 2) * CB + tid < n) id_next = a.point_list[range.x + (b + 2) * CB + tid];
 
         const int cnt = min(CB, n - b * CB);
-        bool warp_done = __all_sync(0xffffffffu, done);
+        const Rec* rec = s_rec[buf];
+        bool warp_done = !__any_sync(0xffffffffu, alive);
         if (!warp_done) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int j = c0 + lane;
                 bool pass = false;
                 if (j < cnt) {
-                    const float4 g0 = s_xyAB[buf][j];
-                    const float4 g1 = s_Cod[buf][j];
+                    const float4 g0 = rec[j].a;
+                    const float4 g1 = rec[j].b;
                     const float q = rect_min_q(g0.z, g0.w, g1.x, g0.x - rx1, g0.x - rx0,
                                                g0.y - ry1, g0.y - ry0);
                     pass = !(q > g1.w);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
+                const uint32_t idx_base = (uint32_t)(b * CB + c0 + 1);
+                // Branch-free body: the kernel is issue-bound and most lanes of a
+                // surviving instance do blend, so predication beats divergence.
                 while (mask) {
-                    const int jj = c0 + __ffs(mask) - 1;
+                    const int bit = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    if (!done) {
-                        const float4 g0 = s_xyAB[buf][jj];
-                        const float4 g1 = s_Cod[buf][jj];
-                        const float dx = g0.x - pixx, dy = g0.y - pixy;
-                        const float power =
-                            -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                        if (!(power > 0.0f)) {
-                            const float alpha = min(0.99f, g1.y * expf(power));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                const float test_T = T * (1 - alpha);
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    const float4 col = s_rgb[buf][jj];
-                                    C0 += col.x * alpha * T;
-                                    C1 += col.y * alpha * T;
-                                    C2 += col.z * alpha * T;
-                                    D += g1.z * alpha * T;
-                                    T = test_T;
-                                    last_contributor = (uint32_t)(b * CB + jj + 1);
-                                }
-                            }
-                        }
-                    }
+                    const Rec& r = rec[c0 + bit];
+                    const float4 g0 = r.a;
+                    const float4 g1 = r.b;
+                    const float4 col = r.c;
+                    const float dx = g0.x - pixx, dy = g0.y - pixy;
+                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    const float alpha = min(0.99f, g1.y * expf(power));
+                    const float test_T = T * (1 - alpha);
+                    // forward.cu:339-354: skip power > 0, skip alpha < 1/255, stop at T < 1e-4
+                    const bool ok = alive && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    const bool stop = ok && (test_T < 0.0001f);
+                    const bool blend = ok && !stop;
+                    const float ae = blend ? alpha : 0.0f;
+                    C0 += col.x * ae * T;
+                    C1 += col.y * ae * T;
+                    C2 += col.z * ae * T;
+                    D += g1.z * ae * T;
+                    T = blend ? test_T : T;
+                    last_contributor = blend ? idx_base + (uint32_t)bit : last_contributor;
+                    alive = alive && !stop;
                 }
-                if (__all_sync(0xffffffffu, done)) {
+                if (!__any_sync(0xffffffffu, alive)) {
                     warp_done = true;
                     break;
                 }
@@ -252,10 +259,14 @@ __device__ __forceinline__ int reduce10_slot(int lane) {
     return r + ((lane & 16) ? 5 : 0);
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs a) {
-    __shared__ __align__(16) float4 s_xyAB[2][CB];
-    __shared__ __align__(16) float4 s_Cod[2][CB];
-    __shared__ __align__(16) float4 s_rgb[2][CB];
+    __shared__ Rec s_rec[2][CB];
     __shared__ uint32_t s_id[2][CB];
     __shared__ uint32_t s_max;
 
@@ -283,7 +294,8 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
         dpix2 = a.dL_dpix[2 * HW + pix_id];
         dpixd = a.dL_dpix_depth[pix_id];
     }
-    const float bg_dot_dpixel = a.bg[0] * dpix0 + a.bg[1] * dpix1 + a.bg[2] * dpix2;
+    // -(T_final * sum_c bg_c dL/dpix_c): the background term of backward.cu:564-567
+    const float nbg = -T_final * (a.bg[0] * dpix0 + a.bg[1] * dpix1 + a.bg[2] * dpix2);
 
     // only instances below the block's deepest contributor matter (backward.cu:513)
     if (tid == 0) s_max = 0;
@@ -299,6 +311,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_depth = 0.f;
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     const int my_slot = reduce10_slot(lane);
+    float* const my_grad = a.grad_rec + (my_slot >= 0 ? my_slot : 0);
 
     // slot t of batch b holds list index m-1-(b*CB+t)
     uint32_t id_next = 0;
@@ -307,9 +320,9 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
         if (i0 >= 0) {
             const uint32_t id = a.point_list[range.x + i0];
             s_id[0][tid] = id;
-            cp_async16(&s_xyAB[0][tid], &a.xyAB[id]);
-            cp_async16(&s_Cod[0][tid], &a.Cod[id]);
-            cp_async16(&s_rgb[0][tid], &a.rgb[id]);
+            cp_async16(&s_rec[0][tid].a, &a.xyAB[id]);
+            cp_async16(&s_rec[0][tid].b, &a.Cod[id]);
+            cp_async16(&s_rec[0][tid].c, &a.rgb[id]);
         }
         cp_async_commit();
         const int i1 = m - 1 - (CB + tid);
@@ -324,9 +337,9 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
             const int i1 = m - 1 - ((b + 1) * CB + tid);
             if (i1 >= 0) {
                 s_id[buf ^ 1][tid] = id_next;
-                cp_async16(&s_xyAB[buf ^ 1][tid], &a.xyAB[id_next]);
-                cp_async16(&s_Cod[buf ^ 1][tid], &a.Cod[id_next]);
-                cp_async16(&s_rgb[buf ^ 1][tid], &a.rgb[id_next]);
+                cp_async16(&s_rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
+                cp_async16(&s_rec[buf ^ 1][tid].b, &a.Cod[id_next]);
+                cp_async16(&s_rec[buf ^ 1][tid].c, &a.rgb[id_next]);
             }
             cp_async_commit();
             const int i2 = m - 1 - ((b + 2) * CB + tid);
@@ -334,14 +347,15 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
         }
         const int top = m - 1 - b * CB;           // list index of slot 0
         const int cnt = min(CB, top + 1);
+        const Rec* rec = s_rec[buf];
         // the warp has nothing to do for instances at or above warp_max
         if (top - (cnt - 1) < warp_max) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
                 const int j = c0 + lane;
                 bool pass = false;
                 if (j < cnt && top - j < warp_max) {
-                    const float4 g0 = s_xyAB[buf][j];
-                    const float4 g1 = s_Cod[buf][j];
+                    const float4 g0 = rec[j].a;
+                    const float4 g1 = rec[j].b;
                     const float q = rect_min_q(g0.z, g0.w, g1.x, g0.x - rx1, g0.x - rx0,
                                                g0.y - ry1, g0.y - ry0);
                     pass = !(q > g1.w);
@@ -351,8 +365,9 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
                     const int jj = c0 + __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int contributor = top - jj;   // 0-based list index
-                    const float4 g0 = s_xyAB[buf][jj];
-                    const float4 g1 = s_Cod[buf][jj];
+                    const Rec& r = rec[jj];
+                    const float4 g0 = r.a;
+                    const float4 g1 = r.b;
                     const float dx = g0.x - pixx, dy = g0.y - pixy;
                     const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                     const float G = expf(power);
@@ -364,44 +379,40 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
 #pragma unroll
                     for (int i = 0; i < 10; ++i) v[i] = 0.f;
                     if (contrib) {
-                        const float4 col = s_rgb[buf][jj];
-                        T = T / (1.f - alpha);
+                        const float4 col = r.c;
+                        // 1/(1-alpha): alpha <= 0.99, approx reciprocal (1 ulp) instead of
+                        // the two IEEE divisions of backward.cu:529,567
+                        const float inv = rcp_approx(1.f - alpha);
+                        T = T * inv;
                         const float w = alpha * T;
-                        float dL_dalpha = 0.0f;
-                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                        lc0 = col.x;
-                        dL_dalpha += (col.x - acc0) * dpix0;
+                        const float om = 1.f - last_alpha;
+                        acc0 = last_alpha * lc0 + om * acc0;
+                        acc1 = last_alpha * lc1 + om * acc1;
+                        acc2 = last_alpha * lc2 + om * acc2;
+                        accd = last_alpha * last_depth + om * accd;
+                        lc0 = col.x; lc1 = col.y; lc2 = col.z; last_depth = g1.z;
+                        float dL_dalpha = (col.x - acc0) * dpix0 + (col.y - acc1) * dpix1 +
+                                          (col.z - acc2) * dpix2 + (g1.z - accd) * dpixd;
                         v[6] = w * dpix0;
-                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                        lc1 = col.y;
-                        dL_dalpha += (col.y - acc1) * dpix1;
                         v[7] = w * dpix1;
-                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                        lc2 = col.z;
-                        dL_dalpha += (col.z - acc2) * dpix2;
                         v[8] = w * dpix2;
-                        const float c_d = g1.z;
-                        accd = last_alpha * last_depth + (1.f - last_alpha) * accd;
-                        last_depth = c_d;
-                        dL_dalpha += (c_d - accd) * dpixd;
                         v[9] = w * dpixd;
-                        dL_dalpha *= T;
+                        dL_dalpha = dL_dalpha * T + nbg * inv;
                         last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
                         const float dL_dG = g1.y * dL_dalpha;
                         const float gdx = G * dx, gdy = G * dy;
                         const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
                         const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+                        const float h = -0.5f * dL_dG;
                         v[0] = dL_dG * dG_ddelx * ddelx_dx;
                         v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = -0.5f * gdx * dx * dL_dG;
-                        v[3] = -0.5f * gdx * dy * dL_dG;
-                        v[4] = -0.5f * gdy * dy * dL_dG;
+                        v[2] = h * gdx * dx;
+                        v[3] = h * gdx * dy;
+                        v[4] = h * gdy * dy;
                         v[5] = G * dL_dalpha;
                     }
                     const float sum = warp_reduce10(v, lane);
-                    if (my_slot >= 0)
-                        atomicAdd(a.grad_rec + (size_t)s_id[buf][jj] * GRAD_REC + my_slot, sum);
+                    if (my_slot >= 0) atomicAdd(my_grad + (size_t)s_id[buf][jj] * GRAD_REC, sum);
                 }
             }
         }

@@ -221,23 +221,73 @@ __device__ __forceinline__ float cull_tau(float opacity, float A, float B, float
     return (tau + 2e-3f) / (1.0f - eps) + 2e-3f;
 }
 
-__global__ void __launch_bounds__(256) preprocess_forward_kernel(PreFwdArgs a) {
-    __shared__ Cam s_cam;
-    load_cam(s_cam, a.view, a.proj, a.campos);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
+// ---- warp-cooperative row staging ------------------------------------------
+// A warp owns 32 consecutive Gaussians, i.e. 32 consecutive rows of L floats
+// (SH coefficients or their gradients: L = 3*M, 192 bytes at M = 16).  Reading
+// or writing them one row per lane touches 32 different 32-byte sectors per
+// instruction; instead the warp moves the contiguous 32*L-float block with
+// fully coalesced (vector) accesses through a shared-memory tile whose row
+// stride is odd, so the per-lane row accesses are bank-conflict free.
+constexpr int PRE_THREADS = 128;
+__host__ __device__ inline int row_stride(int L) { return L | 1; }
 
-    a.radii[idx] = 0;
-    a.tiles_touched[idx] = 0;
-    a.depth_key[idx] = DEPTH_KEY_INVISIBLE;
-    a.order[idx] = (uint32_t)idx;
+template <int LT>   // LT > 0: compile-time row length, 0: runtime
+__device__ __forceinline__ void warp_rows_in(const float* __restrict__ g, float* s, int Lr, int rows,
+                                             int lane) {
+    const int L = LT > 0 ? LT : Lr;
+    const int stride = row_stride(L);
+    const int total = rows * L;
+    if ((L & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int q = lane; q < total / 4; q += 32) {
+            const float4 v = __ldg(g4 + q);
+            const int f = q * 4, r = f / L, j = f - r * L;
+            float* d = s + r * stride + j;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int f = lane; f < total; f += 32) {
+            const int r = f / L, j = f - r * L;
+            s[r * stride + j] = __ldg(g + f);
+        }
+    }
+}
+template <int LT>
+__device__ __forceinline__ void warp_rows_out(float* __restrict__ g, const float* s, int Lr, int rows,
+                                              int lane) {
+    const int L = LT > 0 ? LT : Lr;
+    const int stride = row_stride(L);
+    const int total = rows * L;
+    if ((L & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        for (int q = lane; q < total / 4; q += 32) {
+            const int f = q * 4, r = f / L, j = f - r * L;
+            const float* d = s + r * stride + j;
+            g4[q] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    } else {
+        for (int f = lane; f < total; f += 32) {
+            const int r = f / L, j = f - r * L;
+            g[f] = s[r * stride + j];
+        }
+    }
+}
 
-    const float3 p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+struct Projected {
+    float2 pix;
+    float3 conic;
+    float depth, radius, lam_max, lam_min;
+    unsigned rminx, rminy, rmaxx, rmaxy;
+};
+
+// Everything of forward.cu:182-237 up to (not including) the colour; false = culled.
+__device__ __forceinline__ bool project_gaussian(const PreFwdArgs& a, const Cam& cam, int idx,
+                                                 const float3 p_orig, Projected& o) {
     // near cull (auxiliary.h:152-154)
-    const float3 p_view = xform4x3(p_orig, s_cam.view);
-    if (p_view.z <= 0.2f) return;
+    const float3 p_view = xform4x3(p_orig, cam.view);
+    if (p_view.z <= 0.2f) return false;
 
-    const float4 p_hom = xform4x4(p_orig, s_cam.proj);
+    const float4 p_hom = xform4x4(p_orig, cam.proj);
     const float p_w = 1.0f / (p_hom.w + 0.0000001f);
     const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
 
@@ -251,12 +301,12 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(PreFwdArgs a) {
         cov3d_from_scale_rot(s, a.scale_modifier, q, cov3D);
     }
     const float3 cov =
-        cov2d_ewa(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, s_cam.view);
+        cov2d_ewa(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, cam.view);
 
     const float det = (cov.x * cov.z - cov.y * cov.y);
-    if (det == 0.0f) return;
+    if (det == 0.0f) return false;
     const float det_inv = 1.f / det;
-    const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+    o.conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
 
     const float mid = 0.5f * (cov.x + cov.z);
     const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
@@ -267,34 +317,68 @@ __global__ void __launch_bounds__(256) preprocess_forward_kernel(PreFwdArgs a) {
     // getRect (auxiliary.h:46-56): radius is passed as int, float division, C truncation
     const int max_radius = (int)my_radius;
     const unsigned gx = (unsigned)a.grid_x, gy = (unsigned)a.grid_y;
-    const unsigned rminx = min(gx, (unsigned)max((int)0, (int)((point_image.x - max_radius) / TILE_X)));
-    const unsigned rminy = min(gy, (unsigned)max((int)0, (int)((point_image.y - max_radius) / TILE_Y)));
-    const unsigned rmaxx =
-        min(gx, (unsigned)max((int)0, (int)((point_image.x + max_radius + TILE_X - 1) / TILE_X)));
-    const unsigned rmaxy =
-        min(gy, (unsigned)max((int)0, (int)((point_image.y + max_radius + TILE_Y - 1) / TILE_Y)));
-    if ((rmaxx - rminx) * (rmaxy - rminy) == 0) return;
+    o.rminx = min(gx, (unsigned)max((int)0, (int)((point_image.x - max_radius) / TILE_X)));
+    o.rminy = min(gy, (unsigned)max((int)0, (int)((point_image.y - max_radius) / TILE_Y)));
+    o.rmaxx = min(gx, (unsigned)max((int)0, (int)((point_image.x + max_radius + TILE_X - 1) / TILE_X)));
+    o.rmaxy = min(gy, (unsigned)max((int)0, (int)((point_image.y + max_radius + TILE_Y - 1) / TILE_Y)));
+    if ((o.rmaxx - o.rminx) * (o.rmaxy - o.rminy) == 0) return false;
+    o.pix = point_image;
+    o.depth = p_view.z;
+    o.radius = my_radius;
+    o.lam_max = max(lambda1, lambda2);
+    o.lam_min = min(lambda1, lambda2);
+    return true;
+}
 
-    float3 col;
+template <int MT>   // MT = 16: SH rows of 48 floats known at compile time; 0: runtime M
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(PreFwdArgs a) {
+    extern __shared__ float s_dyn[];
+    __shared__ Cam s_cam;
+    load_cam(s_cam, a.view, a.proj, a.campos);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = idx < a.P;
+
+    Projected po;
+    float3 p_orig = {0.f, 0.f, 0.f};
+    bool vis = false;
+    if (valid) {
+        a.radii[idx] = 0;
+        a.tiles_touched[idx] = 0;
+        a.depth_key[idx] = DEPTH_KEY_INVISIBLE;
+        a.order[idx] = (uint32_t)idx;
+        p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
+        vis = project_gaussian(a, s_cam, idx, p_orig, po);
+    }
+
+    float3 col = {0.f, 0.f, 0.f};
     uint8_t clamped = 0;
     if (a.colors_precomp == nullptr) {
-        col = sh_to_rgb(a.D, p_orig, s_cam.campos, a.shs + (size_t)idx * a.M * 3, clamped);
-    } else {
+        if (__any_sync(0xffffffffu, vis)) {
+            const int L = 3 * (MT > 0 ? MT : a.M);
+            float* rows = s_dyn + warp * 32 * row_stride(L);
+            const int first = idx - lane;
+            const int nrows = min(32, a.P - first);
+            warp_rows_in<3 * MT>(a.shs + (size_t)first * L, rows, L, nrows, lane);
+            __syncwarp();
+            if (vis) col = sh_to_rgb(a.D, p_orig, s_cam.campos, rows + lane * row_stride(L), clamped);
+        }
+    } else if (vis) {
         col = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
     }
+    if (!vis) return;
     const float opacity = a.opacities[idx];
 
     a.clamped[idx] = clamped;
-    a.radii[idx] = (int)my_radius;
-    a.depth_key[idx] = __float_as_uint(p_view.z);
-    a.xyAB[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-    a.Cod[idx] = make_float4(conic.z, opacity, p_view.z,
-                             cull_tau(opacity, conic.x, conic.y, conic.z, max(lambda1, lambda2),
-                                      min(lambda1, lambda2)));
+    a.radii[idx] = (int)po.radius;
+    a.depth_key[idx] = __float_as_uint(po.depth);
+    a.xyAB[idx] = make_float4(po.pix.x, po.pix.y, po.conic.x, po.conic.y);
+    a.Cod[idx] = make_float4(po.conic.z, opacity, po.depth,
+                             cull_tau(opacity, po.conic.x, po.conic.y, po.conic.z, po.lam_max, po.lam_min));
     a.rgb[idx] = make_float4(col.x, col.y, col.z, 0.f);
-    a.rect[idx] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
-                               (unsigned short)rmaxy);
-    a.tiles_touched[idx] = (rmaxy - rminy) * (rmaxx - rminx);
+    a.rect[idx] = make_ushort4((unsigned short)po.rminx, (unsigned short)po.rminy, (unsigned short)po.rmaxx,
+                               (unsigned short)po.rmaxy);
+    a.tiles_touched[idx] = (po.rmaxy - po.rminy) * (po.rmaxx - po.rminx);
 }
 
 // rasterizer_impl.cu:54-66
@@ -350,15 +434,30 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {   // auxiliar
     return r;
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) {
+template <int MT>   // MT = 16: compile-time SH row length; 0: runtime M
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(PreBwdArgs a) {
+    extern __shared__ float s_dyn[];
     __shared__ Cam s_cam;
     load_cam(s_cam, a.view, a.proj, a.campos);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.P) return;
+    const int idx_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = idx_raw < a.P;
+    const int idx = valid ? idx_raw : a.P - 1;   // clamped for address arithmetic only
     const float* view = s_cam.view;
     const float* proj = s_cam.proj;
 
-    const bool visible = a.radii[idx] > 0;
+    const bool visible = valid && a.radii[idx] > 0;
+    // SH rows (input coefficients, then reused for their gradients) staged per warp
+    const int Msh = MT > 0 ? MT : a.M;
+    const int L = 3 * Msh;
+    float* rows = s_dyn + warp * 32 * row_stride(L);
+    float* myrow = rows + lane * row_stride(L);
+    const int first = idx_raw - lane;
+    const int nrows = min(32, a.P - first);
+    if (a.shs) {
+        if (__any_sync(0xffffffffu, visible)) warp_rows_in<3 * MT>(a.shs + (size_t)first * L, rows, L, nrows, lane);
+        __syncwarp();
+    }
     float g[GRAD_REC];
     if (visible) {
         const float4* gr = reinterpret_cast<const float4*>(a.grad_rec + (size_t)idx * GRAD_REC);
@@ -371,6 +470,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
 #pragma unroll
         for (int i = 0; i < GRAD_REC; ++i) g[i] = 0.f;
     }
+    if (valid) {
     // outputs that are plain copies of the composite's accumulators
     a.dL_dmean2D[3 * idx + 0] = g[0];
     a.dL_dmean2D[3 * idx + 1] = g[1];
@@ -386,6 +486,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
     a.dL_dcolor[3 * idx + 1] = g[7];
     a.dL_dcolor[3 * idx + 2] = g[8];
     if (a.dL_ddepth) a.dL_ddepth[idx] = g[9];
+    }
 
     float dmean[3] = {0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -393,10 +494,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
     float drot[4] = {0.f, 0.f, 0.f, 0.f};
 
     if (!visible) {
-        if (a.dL_dsh) {
-            float* o = a.dL_dsh + (size_t)idx * a.M * 3;
-            for (int i = 0; i < a.M * 3; ++i) o[i] = 0.f;
-        }
+        if (a.dL_dsh)
+            for (int i = 0; i < L; ++i) myrow[i] = 0.f;
     } else {
         const float3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
         float cov3D[6];
@@ -506,8 +605,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
         }
         // ---- SH (backward.cu:20-139) ---------------------------------------
         if (a.shs) {
-            const float* sh = a.shs + (size_t)idx * a.M * 3;
-            float* dsh = a.dL_dsh + (size_t)idx * a.M * 3;
+            const float* sh = myrow;   // staged coefficients; overwritten with dL/dsh below
+            float* dsh = myrow;
             const float* campos = s_cam.campos;
             const float3 dir_orig = {mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]};
             const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -539,11 +638,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
                         nb = 16;
                     }
                 }
-            }
-            for (int i = 0; i < a.M; ++i) {
-                float b = i < nb ? basis[i] : 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) dsh[i * 3 + c] = b * dRGB[c];
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -580,6 +674,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
             }
             const float3 dm = dnormvdv3(dir_orig, make_float3(ddir[0], ddir[1], ddir[2]));
             dmean[0] += dm.x; dmean[1] += dm.y; dmean[2] += dm.z;
+            // all reads of this lane's coefficients are done: the row now carries dL/dsh
+            for (int i = 0; i < Msh; ++i) {
+                float b = i < nb ? basis[i] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dsh[i * 3 + c] = b * dRGB[c];
+            }
         }
         // ---- cov3D -> scale, rotation (backward.cu:278-341) ----------------
         if (a.scales) {
@@ -618,6 +718,11 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
                       2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
         }
     }
+    if (a.dL_dsh) {   // coalesced write-out of the warp's 32 gradient rows (zeros where invisible)
+        __syncwarp();
+        if (nrows > 0) warp_rows_out<3 * MT>(a.dL_dsh + (size_t)first * L, rows, L, nrows, lane);
+    }
+    if (!valid) return;
     // like the reference, dL_dscale is taken w.r.t. (scale_modifier * scale) and is
     // not multiplied by the modifier (backward.cu:322-325)
     a.dL_dmean3D[3 * idx + 0] = dmean[0];

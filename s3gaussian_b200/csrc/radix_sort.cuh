@@ -18,19 +18,19 @@ namespace s3g {
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
     uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -70,6 +70,7 @@ sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int begin_b
 constexpr uint32_t LB_FLAG_AGG = 1u << 30;
 constexpr uint32_t LB_FLAG_INCL = 2u << 30;
 constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1u;
+constexpr int LB_WINDOW = 8;
 
 // block-wide exclusive scan of one value per thread (256 threads)
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/,
@@ -126,14 +127,17 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         uint32_t idx = base + i * 32 + lane;
         k[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
     }
-    // warp-level multisplit ranking
+    // warp-level multisplit ranking; the 16 MATCHes are independent and issued
+    // back to back, only the counter updates form a chain
     uint32_t rank[SORT_ITEMS];
     const uint32_t lt = lanemask_lt();
 #pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) rank[i] = __match_any_sync(0xffffffffu, (k[i] >> shift) & mask);
+#pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t d = (k[i] >> shift) & mask;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
+        const uint32_t d = (k[i] >> shift) & mask;
+        const uint32_t peers = rank[i];
+        const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader) {
             old = s_wc[warp][d];
@@ -160,16 +164,31 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const uint32_t hexcl = block_excl_scan_256(hist[tid], s_warp);
     s_dstart[tid] = dstart;
 
+    // Decoupled look-back, windowed: LB_WINDOW predecessor words are fetched with
+    // independent loads per round trip (one serial L2 hop per predecessor made the
+    // chain, not the data movement, the critical path of the pass).
     uint32_t excl = 0;
     if (bid > 0) {
-        const uint32_t* p = status + (size_t)(bid - 1) * RADIX + tid;
-        while (true) {
-            uint32_t v = ld_volatile_u32(p);
-            uint32_t f = v >> 30;
-            if (f == 0) continue;
-            excl += v & LB_VALUE_MASK;
-            if (f == 2) break;
-            p -= RADIX;
+        int p = (int)bid - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t v[LB_WINDOW];
+#pragma unroll
+            for (int k = 0; k < LB_WINDOW; ++k)
+                v[k] = (p - k >= 0) ? ld_volatile_u32(status + (size_t)(p - k) * RADIX + tid) : LB_FLAG_INCL;
+#pragma unroll
+            for (int k = 0; k < LB_WINDOW; ++k) {
+                if (done) break;
+                const uint32_t f = v[k] >> 30;
+                if (f == 0) {          // not published yet: retry from here
+                    p -= k;
+                    goto next_round;
+                }
+                excl += v[k] & LB_VALUE_MASK;
+                if (f == 2) done = true;
+            }
+            p -= LB_WINDOW;
+        next_round:;
         }
         st_volatile_u32(my_status, LB_FLAG_INCL | (excl + count));
     }

@@ -32,7 +32,8 @@ def cpu_deep_copy_tuple(input_tuple):
 
 class _Arena:
     """A growable device byte buffer handed to the C side as an s3g_alloc_fn
-    (what resizeFunctional() does with a torch tensor, rasterize_points.cu:27-33)."""
+    (what resizeFunctional() does with a torch tensor, rasterize_points.cu:27-33).
+    It only ever grows, so a recycled arena makes no allocator traffic."""
 
     def __init__(self, device):
         self.device = device
@@ -41,10 +42,51 @@ class _Arena:
 
     def _alloc(self, _user, nbytes):
         try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            nbytes = int(nbytes)
+            if self.tensor.numel() < nbytes:
+                # 12 % headroom: num_rendered moves a little from view to view
+                self.tensor = None
+                self.tensor = torch.empty(nbytes + nbytes // 8, dtype=torch.uint8, device=self.device)
             return self.tensor.data_ptr()
         except Exception:   # pragma: no cover - surfaced as S3G_ERR_ALLOC
             return 0
+
+
+class _ArenaSet:
+    """The three opaque state buffers of one forward (geometry, binning, image)."""
+    __slots__ = ("geom", "binning", "img", "key")
+
+    def __init__(self, device, key):
+        self.geom, self.binning, self.img, self.key = _Arena(device), _Arena(device), _Arena(device), key
+
+
+# Recycling pool.  The reference allocates three fresh byte tensors per forward
+# (rasterize_points.cu:72-79); at 2M Gaussians that is ~0.5 GB of differently
+# sized blocks per step interleaved with the gradient tensors, which fragments
+# torch's caching allocator into one cudaMalloc (~15 ms) per step.  A set is
+# leased to one autograd node and comes back when that node dies; reuse is
+# ordered by the CUDA stream, so the pool is keyed by (device, stream).
+_POOL: dict = {}
+_POOL_MAX_FREE = 4
+
+
+class _Lease:
+    def __init__(self, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        free = _POOL.setdefault(key, [])
+        self.aset = free.pop() if free else _ArenaSet(device, key)
+
+    def __del__(self):
+        aset, self.aset = self.aset, None
+        if aset is not None and _POOL is not None:
+            free = _POOL.setdefault(aset.key, [])
+            if len(free) < _POOL_MAX_FREE:
+                free.append(aset)
+
+
+def release_cached_arenas():
+    """Drop all pooled state buffers (they are plain torch tensors)."""
+    _POOL.clear()
 
 
 def _ptr(t: torch.Tensor | None):
@@ -104,7 +146,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+        lease = _Lease(dev)
+        geom, binning, img = lease.aset.geom, lease.aset.binning, lease.aset.img
         M = sh.size(1) if sh.numel() != 0 else 0
 
         args = (geom.cb, None, binning.cb, None, img.cb, None, P, int(rs.sh_degree), M, _ptr(bg), W, H,
@@ -131,6 +174,10 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         ctx.raster_settings = rs
         ctx.num_rendered = int(num_rendered)
+        # the three state buffers stay with the lease (not save_for_backward: they are ours,
+        # opaque and recycled); saved[7:10] keeps the reference's tuple layout for callers
+        # that peek at it
+        ctx.lease = lease
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
                               geom.tensor, binning.tensor, img.tensor)
         ctx.mark_non_differentiable(radii)

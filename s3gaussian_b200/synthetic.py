@@ -167,7 +167,7 @@ def make_cloud(P: int, seed: int = 0, width=1920, height=1280) -> GaussianCloud:
 
 
 def make_small_scene(P=256, width=64, height=48, seed=1):
-    """A tiny scene for oracle-sized tests: one camera looking down +x at a blob."""
+    """A tiny scene for CPU-checkable tests: one camera looking down +x at a blob."""
     g = torch.Generator().manual_seed(seed)
     cam = make_camera(width, height, (0.0, 0.0, 0.0), focal=0.9 * width)
     xyz = torch.stack([2.0 + 6.0 * torch.rand(P, generator=g),

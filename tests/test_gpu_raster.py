@@ -1,0 +1,308 @@
+"""GPU parity tests of the rasterizer path (run with -m gpu on the B200 box).
+
+Every call goes through the C ABI of libs3g_b200.so (via the drop-in Python
+module).  Three checkers, in order of authority:
+  1. tests/golden/raster_*.npz - outputs of the real reference extension;
+  2. the real reference extension itself (oracle/_ref, prebuilt, travels to the box);
+  3. the CPU oracle (oracle/splat_oracle.c), pinned by (1) in test_oracle_golden.py.
+Bars: bit-exact for radii / tiles_touched / sorted point_list / tile keys /
+ranges / n_contrib; 1e-4 relative (of the tensor max) for colour, depth and all
+gradients, as north_star states.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_ext
+import util
+from test_oracle_golden import GOLD, load_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ours(built_lib):
+    from s3gaussian_b200 import diff_gaussian_rasterization as m
+    return m
+
+
+def check_state_vs(views, radii, R, ref_state):
+    """ref_state: dict(num_rendered, radii, tiles_touched, point_list, keys(u64), ranges, n_contrib)"""
+    assert R == int(ref_state["num_rendered"])
+    np.testing.assert_array_equal(radii.cpu().numpy(), ref_state["radii"])
+    np.testing.assert_array_equal(views["tiles_touched"], ref_state["tiles_touched"])
+    np.testing.assert_array_equal(views["point_list"], ref_state["point_list"])
+    np.testing.assert_array_equal(views["point_list_tiles"],
+                                  (ref_state["keys"] >> np.uint64(32)).astype(np.uint32))
+    np.testing.assert_array_equal(views["ranges"], ref_state["ranges"])
+    np.testing.assert_array_equal(views["n_contrib"], ref_state["n_contrib"])
+
+
+# --------------------------------------------------------------------- golden
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[7:-4] for p in GOLD])
+def test_cuda_matches_reference_golden(path, ours):
+    z, d = load_case(path)
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    check_state_vs(views, radii, R, dict(num_rendered=z["num_rendered"], radii=z["radii"],
+                                         tiles_touched=z["tiles_touched"], point_list=z["point_list"],
+                                         keys=z["point_list_keys"], ranges=z["ranges"],
+                                         n_contrib=z["n_contrib"]))
+    vis = z["radii"] > 0
+    # projected state: bit-exact against the reference (same expression trees, same FMA contraction)
+    np.testing.assert_array_equal(views["xyAB"][vis, :2].view(np.uint32), z["means2D"][vis].view(np.uint32))
+    conic = np.stack([views["xyAB"][:, 2], views["xyAB"][:, 3], views["Cod"][:, 0], views["Cod"][:, 1]], 1)
+    np.testing.assert_array_equal(conic[vis].view(np.uint32), z["conic_opacity"][vis].view(np.uint32))
+    np.testing.assert_array_equal(views["Cod"][vis, 2].view(np.uint32), z["depths"][vis].view(np.uint32))
+    assert util.relerr(color.cpu().numpy(), z["color"]) < TOL
+    assert util.relerr(depth.cpu().numpy(), z["depth"]) < TOL
+    assert util.relerr(views["final_T"], z["final_T"]) < TOL
+    # gradients
+    gc, gd = torch.from_numpy(z["in_grad_color"]), torch.from_numpy(z["in_grad_depth"])
+    out = util.run_module(ours, d, DEV, gc, gd)
+    n = 0
+    for k, g in out["grads"].items():
+        key = "grad_" + k
+        if key in z.files:
+            assert util.relerr(g.cpu().numpy(), z[key]) < TOL, (k, util.relerr(g.cpu().numpy(), z[key]))
+            n += 1
+    assert n >= 5
+
+
+# --------------------------------------------------------------------- oracle
+@pytest.mark.parametrize("mode,deg,P,W,H,seed", [
+    ("sh", 3, 400, 80, 64, 11), ("sh", 0, 257, 33, 17, 12), ("rgb", 0, 1000, 128, 96, 13),
+    ("sh", 2, 64, 16, 16, 14), ("rgb", 0, 1, 40, 40, 15)])
+def test_cuda_matches_cpu_oracle(mode, deg, P, W, H, seed, ours, oracle_lib):
+    from s3gaussian_b200 import synthetic as syn
+    cloud, cam = syn.make_small_scene(P=P, width=W, height=H, seed=seed)
+    d = util.scene_inputs(cloud, cam, mode=mode, sh_degree=deg)
+    gc, gd = util.seeded_grads(d, seed)
+    o = util.oracle_run(oracle_lib, d, gc, gd)
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
+                                         tiles_touched=o["geometry"]["tiles_touched"],
+                                         point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                                         ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
+    assert util.relerr(depth.cpu().numpy(), o["depth"]) < TOL
+    out = util.run_module(ours, d, DEV, gc, gd)
+    names = {"means3D": "means3D", "means2D": "means2D", "opacities": "opacity", "scales": "scales",
+             "rotations": "rotations", "shs": "sh", "colors_precomp": "colors"}
+    for k, g in out["grads"].items():
+        ref = o["grads"][names[k]].reshape(g.shape)
+        if np.abs(ref).max() == 0:
+            assert float(g.abs().max()) == 0
+        else:
+            assert util.relerr(g.cpu().numpy(), ref) < TOL, (k, util.relerr(g.cpu().numpy(), ref))
+
+
+# ------------------------------------------------------------ real reference
+def _need_ref():
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref (prebuilt reference extension) not present")
+    return ref_ext.load()
+
+
+@pytest.mark.parametrize("P,W,H,mode", [(100_000, 960, 640, "sh"), (100_000, 960, 640, "rgb"),
+                                        (500_000, 1920, 1280, "rgb"), (2_000_000, 1920, 1280, "sh")])
+def test_cuda_matches_reference_extension_at_benchmark_sizes(P, W, H, mode, ours):
+    """BASELINE configs 2-4 geometry: identical Gaussians + camera through both
+    implementations; integer state bit-exact, floats within 1e-4."""
+    from s3gaussian_b200 import synthetic as syn
+    ref = _need_ref()
+    cloud = syn.make_cloud(P, seed=0)
+    cam = syn.make_camera(W, H, (0, 0, 2.0))
+    d = util.scene_inputs(cloud, cam, mode=mode, sh_degree=3, bg=(0.0, 0.0, 0.0))
+    gc, gd = util.seeded_grads(d, 7)
+    r = util.run_module(ref, d, DEV, gc, gd)
+    m = util.run_module(ours, d, DEV, gc, gd)
+    assert torch.equal(r["radii"], m["radii"])
+    assert util.relerr(m["color"].cpu().numpy(), r["color"].cpu().numpy()) < TOL
+    assert util.relerr(m["depth"].cpu().numpy(), r["depth"].cpu().numpy()) < TOL
+    for k in r["grads"]:
+        e = util.relerr(m["grads"][k].cpu().numpy(), r["grads"][k].cpu().numpy())
+        assert e < TOL, (k, e)
+    # internal state bit for bit
+    E = torch.Tensor([])
+    g = lambda k: d[k].to(DEV).contiguous() if d[k] is not None else E
+    R0, _, _, _, gb, bb, ib = ref._C.rasterize_gaussians(
+        d["bg"].to(DEV), g("means3D"), g("colors_precomp"), g("opacities"), g("scales"), g("rotations"), 1.0,
+        g("cov3D_precomp"), d["viewmatrix"].to(DEV), d["projmatrix"].to(DEV), d["tanfovx"], d["tanfovy"], H, W,
+        g("shs"), 3, d["campos"].to(DEV), False, False)
+    torch.cuda.synchronize()
+    rg, rb, ri = ref_ext.decode_geom(gb, P), ref_ext.decode_binning(bb, R0), ref_ext.decode_image(ib, W * H)
+    del gb, bb, ib
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    check_state_vs(views, radii, R, dict(num_rendered=R0, radii=r["radii"].cpu().numpy(),
+                                         tiles_touched=rg["tiles_touched"], point_list=rb["point_list"],
+                                         keys=rb["point_list_keys"], ranges=ri["ranges"].reshape(-1, 2)[:tiles],
+                                         n_contrib=ri["n_contrib"]))
+
+
+def test_mark_visible_matches_reference_and_oracle(ours, oracle_lib):
+    from s3gaussian_b200 import synthetic as syn
+    cloud = syn.make_cloud(50_000, seed=3)
+    cam = syn.make_camera(640, 480, (0, 0, 2.0), yaw_deg=20)
+    d = util.scene_inputs(cloud, cam, mode="rgb")
+    mine = ours.GaussianRasterizer(util.settings_for(ours, d, DEV)).markVisible(d["means3D"].to(DEV))
+    assert mine.dtype == torch.bool
+    exp = oracle_lib.mark_visible(d["means3D"].numpy(), d["viewmatrix"].numpy())
+    np.testing.assert_array_equal(mine.cpu().numpy(), exp)
+    if ref_ext.available():
+        ref = ref_ext.load()
+        theirs = ref.GaussianRasterizer(util.settings_for(ref, d, DEV)).markVisible(d["means3D"].to(DEV))
+        assert torch.equal(mine, theirs)
+
+
+# ------------------------------------------------------------ edge cases
+def test_empty_cloud_and_all_culled(ours):
+    from s3gaussian_b200 import synthetic as syn
+    cloud, cam = syn.make_small_scene(P=8, width=40, height=24, seed=2)
+    d = util.scene_inputs(cloud, cam, mode="rgb")
+    # P == 0: outputs stay zero like the reference glue (rasterize_points.cu:82)
+    d0 = dict(d)
+    for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp"):
+        d0[k] = d[k][:0]
+    out = util.run_module(ours, d0, DEV)
+    assert out["radii"].numel() == 0 and float(out["color"].abs().max()) == 0
+    # everything behind the camera: R == 0, colour == background, depth == 0, zero grads
+    d1 = dict(d)
+    d1["means3D"] = d["means3D"].clone()
+    d1["means3D"][:, 0] = -5.0
+    gc, gd = util.seeded_grads(d1, 3)
+    out = util.run_module(ours, d1, DEV, gc, gd)
+    assert int((out["radii"] > 0).sum()) == 0
+    bg = d1["bg"].view(3, 1, 1).to(DEV)
+    assert torch.equal(out["color"], bg.expand_as(out["color"]).contiguous())
+    assert float(out["depth"].abs().max()) == 0
+    for k, g in out["grads"].items():
+        assert float(g.abs().max()) == 0, k
+
+
+def test_huge_gaussian_covers_every_tile(ours, oracle_lib):
+    """one splat whose rect is the whole grid (cooperative emission path) + small ones"""
+    from s3gaussian_b200 import synthetic as syn
+    cloud, cam = syn.make_small_scene(P=40, width=200, height=120, seed=9)
+    cloud.scaling[0] = 2.0          # exp(2) m: fills the screen
+    cloud.xyz[0] = torch.tensor([6.0, 0.0, 0.0])
+    d = util.scene_inputs(cloud, cam, mode="sh", sh_degree=1)
+    gc, gd = util.seeded_grads(d, 4)
+    o = util.oracle_run(oracle_lib, d, gc, gd)
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    assert views["tiles_touched"][0] == 13 * 8
+    check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
+                                         tiles_touched=o["geometry"]["tiles_touched"],
+                                         point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                                         ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
+
+
+def test_extreme_opacity_and_anisotropy(ours, oracle_lib):
+    """opacity below 1/255 (never blends), opacity ~1 (alpha clamps at 0.99), needle-shaped
+    splats (cull threshold falls back to 'never cull')"""
+    from s3gaussian_b200 import synthetic as syn
+    cloud, cam = syn.make_small_scene(P=300, width=96, height=64, seed=21)
+    cloud.opacity[:60] = -8.0        # sigmoid ~ 3e-4 < 1/255
+    cloud.opacity[60:120] = 12.0     # ~ 1.0
+    cloud.scaling[120:180, 0] += 3.0  # needles
+    cloud.scaling[120:180, 1] -= 2.0
+    d = util.scene_inputs(cloud, cam, mode="rgb")
+    gc, gd = util.seeded_grads(d, 5)
+    o = util.oracle_run(oracle_lib, d, gc, gd)
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
+                                         tiles_touched=o["geometry"]["tiles_touched"],
+                                         point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                                         ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
+    # In this regime (alpha clamped at 0.99, T divided by 0.01 per layer) the gradients are
+    # ill-conditioned: the reference itself moves by ~2e-3 between runs (unordered fp32
+    # atomics, backward.cu:550-587) and sits ~2e-3..6e-3 from the double-accumulating oracle,
+    # so the bar here is 2e-2 against the oracle and "as close as the reference is to itself"
+    # against the reference extension.
+    out = util.run_module(ours, d, DEV, gc, gd)
+    names = {"means3D": "means3D", "opacities": "opacity", "scales": "scales", "rotations": "rotations",
+             "colors_precomp": "colors", "means2D": "means2D"}
+    for k, ok in names.items():
+        e = util.relerr(out["grads"][k].cpu().numpy(), o["grads"][ok].reshape(out["grads"][k].shape))
+        assert e < 2e-2, (k, e)
+    if ref_ext.available():
+        ref = ref_ext.load()
+        r1 = util.run_module(ref, d, DEV, gc, gd)
+        r2 = util.run_module(ref, d, DEV, gc, gd)
+        for k in names:
+            noise = util.relerr(r1["grads"][k].cpu().numpy(), r2["grads"][k].cpu().numpy())
+            e = util.relerr(out["grads"][k].cpu().numpy(), r1["grads"][k].cpu().numpy())
+            assert e < max(5 * noise, TOL), (k, e, noise)
+
+
+# ------------------------------------------- size-independent properties, full size
+def test_full_size_properties(ours):
+    """2M Gaussians, 1920x1280 (BASELINE metric size): sortedness, range consistency,
+    checksum of counts, determinism of the forward, linearity of the backward."""
+    from s3gaussian_b200 import synthetic as syn
+    P, W, H = 2_000_000, 1920, 1280
+    cloud = syn.make_cloud(P, seed=0)
+    cam = syn.make_camera(W, H, (0, 0, 2.0))
+    d = util.scene_inputs(cloud, cam, mode="rgb", bg=(0.0, 0.0, 0.0))
+    color, radii, depth, R, v = util.ours_forward_state(d, DEV)
+    tt, pl, plt, rng = v["tiles_touched"], v["point_list"], v["point_list_tiles"], v["ranges"]
+    assert int(tt.astype(np.int64).sum()) == R                       # checksum of counts
+    assert np.array_equal((tt > 0), radii.cpu().numpy() > 0)
+    assert np.all(np.diff(plt.astype(np.int64)) >= 0)                 # sorted by tile
+    depth_bits = v["Cod"][:, 2].view(np.uint32)[pl].astype(np.int64)
+    key = (plt.astype(np.int64) << 32) | depth_bits
+    assert np.all(np.diff(key) >= 0)                                  # then by depth bits
+    ties = np.diff(key) == 0
+    assert np.all(np.diff(pl.astype(np.int64))[ties] > 0)             # stable: ties keep index order
+    counts = np.bincount(plt, minlength=rng.shape[0])
+    lens = (rng[:, 1].astype(np.int64) - rng[:, 0].astype(np.int64))
+    assert np.array_equal(lens, counts)                               # ranges == histogram
+    nz = counts > 0
+    assert np.array_equal(rng[nz, 0], (np.cumsum(counts) - counts)[nz].astype(np.uint32))
+    assert np.all(rng[~nz] == 0)
+    assert np.all(v["n_contrib"].reshape(H, W) <= lens.reshape(80, 120).repeat(16, 0).repeat(16, 1))
+    # determinism of the forward (bitwise)
+    color2, radii2, depth2, R2, v2 = util.ours_forward_state(d, DEV)
+    assert R2 == R and torch.equal(color, color2) and torch.equal(depth, depth2)
+    assert np.array_equal(v2["point_list"], pl)
+    # linearity of the backward in dL/dout
+    g1c, g1d = util.seeded_grads(d, 1)
+    g2c, g2d = util.seeded_grads(d, 2)
+    a = util.run_module(ours, d, DEV, g1c, g1d)["grads"]
+    b = util.run_module(ours, d, DEV, g2c, g2d)["grads"]
+    c = util.run_module(ours, d, DEV, g1c + 2 * g2c, g1d + 2 * g2d)["grads"]
+    for k in a:
+        lin = (a[k].double() + 2 * b[k].double())
+        e = float((c[k].double() - lin).abs().max() / (lin.abs().max() + 1e-30))
+        assert e < 5e-4, (k, e)
+
+
+def test_radix_sort_standalone(built_lib):
+    """the hand-written onesweep sort vs torch.sort(stable=True), incl. ragged sizes"""
+    import ctypes as C
+    from s3gaussian_b200 import _lib
+    lib = built_lib
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for n, b0, b1, hi in [(1, 0, 32, 2**31), (33, 0, 8, 200), (4096, 0, 32, 2**31), (4097, 0, 14, 9600),
+                          (123_457, 3, 17, 2**20), (1_000_003, 0, 14, 9600), (2_000_000, 0, 32, 2**31)]:
+        keys = torch.randint(0, hi, (n,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+        vals = torch.arange(n, device=DEV, dtype=torch.int32)
+        ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+        tmp = torch.empty(lib.s3g_sort_temp_bytes(n), dtype=torch.uint8, device=DEV)
+        kin, vin = keys.clone(), vals.clone()
+        _lib.check(lib.s3g_sort_pairs_u32(n, kin.data_ptr(), vin.data_ptr(), ko.data_ptr(), vo.data_ptr(), b0, b1,
+                                          tmp.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "sort")
+        torch.cuda.synchronize()
+        dig = (keys.to(torch.int64) >> b0) & ((1 << (b1 - b0)) - 1)
+        _, perm = torch.sort(dig, stable=True)
+        assert torch.equal(vo.to(torch.int64), perm), (n, b0, b1)
+        assert torch.equal(ko, keys[perm])

@@ -180,3 +180,51 @@ def make_small_scene(P=256, width=64, height=48, seed=1):
                           (0.2 * torch.randn(P, 15, 3, generator=g)).float(), torch.log(s).float(),
                           torch.randn(P, 4, generator=g).float(), torch.log(op / (1 - op)).float())
     return cloud, cam
+
+
+# ---------------------------------------------------------------------------
+# HexPlane + decoder parameters (reference state_dict names, scene/deformation.py,
+# scene/hexplane.py:48-70).  Seeded and frozen like the clouds.
+# ---------------------------------------------------------------------------
+DEFAULT_RESOLUTION = (64, 64, 64, 25)       # arguments/__init__.py:218-223
+DEFAULT_MULTIRES = (1, 2, 4, 8)
+PLANE_COMBS = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+WAYMO_AABB = ((80.0, 40.0, 15.0), (-20.0, -40.0, -5.0))   # set_aabb(xyz_max, xyz_min), scene/__init__.py:150-151
+
+
+def make_deform_state(seed=0, resolution=DEFAULT_RESOLUTION, multires=DEFAULT_MULTIRES, width=64, feat_dim=32,
+                      aabb=WAYMO_AABB, all_heads=True, weight_scale=1.0):
+    """state_dict of the reference's deform_network (the keys the hot path reads).
+
+    Spatial planes ~ U(0.1,0.5), time planes near 1 with a small perturbation (so the
+    time coordinate matters), Linear layers Xavier-like; `weight_scale` shrinks the last
+    layers so the synthetic deformations stay realistic (cm-scale)."""
+    g = torch.Generator().manual_seed(seed)
+    st = {"deformation_net.grid.aabb": torch.tensor(aabb, dtype=torch.float32)}
+    for li, m in enumerate(multires):
+        reso = [r * m for r in resolution[:3]] + [resolution[3]]
+        for ci, (a, b) in enumerate(PLANE_COMBS):
+            shape = (1, feat_dim, reso[b], reso[a])
+            if 3 in (a, b):
+                pl = 1.0 + 0.1 * (torch.rand(shape, generator=g) - 0.5)
+            else:
+                pl = 0.1 + 0.4 * torch.rand(shape, generator=g)
+            st[f"deformation_net.grid.grids.{li}.{ci}"] = pl.float()
+
+    def lin(name, fan_out, fan_in, scale=1.0):
+        bound = scale * math.sqrt(6.0 / (fan_in + fan_out))
+        st[name + ".weight"] = ((torch.rand(fan_out, fan_in, generator=g) * 2 - 1) * bound).float()
+        st[name + ".bias"] = ((torch.rand(fan_out, generator=g) * 2 - 1) / math.sqrt(fan_in) * scale).float()
+
+    D = feat_dim * len(multires)
+    lin("deformation_net.feature_out.0", width, D)
+    heads = [("pos_deform", 3), ("shs_deform", 48)]
+    if all_heads:
+        heads += [("scales_deform", 3), ("rotations_deform", 4), ("opacity_deform", 1)]
+    for name, k in heads:
+        lin(f"deformation_net.{name}.1", width, width)
+        lin(f"deformation_net.{name}.3", k, width, weight_scale)
+    lin("deformation_net.dino_head.0", width, width)
+    lin("deformation_net.dino_head.2", width, width)
+    lin("deformation_net.dino_head.4", 3, width, weight_scale)
+    return st

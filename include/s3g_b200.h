@@ -43,6 +43,7 @@ extern "C" {
 #endif
 
 #define S3G_ABI_VERSION 1
+#define S3G_ERR_UNSUPPORTED (-5) /* configuration outside what the kernels are built for */
 
 #define S3G_OK 0
 #define S3G_ERR_ARG (-1)    /* bad argument (maps to the AT_ERROR / Exception paths of the reference glue) */
@@ -155,6 +156,72 @@ int s3g_state_field(int buffer, const char* name, int64_t P, int64_t R, int widt
 size_t s3g_geom_bytes(int64_t P);
 size_t s3g_binning_bytes(int64_t R);
 size_t s3g_image_bytes(int width, int height);
+
+/* ---- HexPlane + deformation decoder + render() front-end -------------------
+ * Replaces, fused into one forward and one backward kernel (csrc/deform.cuh):
+ *   deform_network.forward_dynamic / Deformation.forward_dynamic   scene/deformation.py:108-166,216-231
+ *   HexPlaneField.get_density / interpolate_ms_features             scene/hexplane.py:73-106,160-175
+ *   scaling/rotation/opacity activations + convert_SHs_python      gaussian_renderer/__init__.py:99-117,
+ *                                                                  scene/gaussian_model.py:39-47, utils/sh_utils.py:57-112
+ * Planes are CHANNELS-LAST: plane (a,b) of a level is float[res_b][res_a][32], i.e. the
+ * reference's [1,32,res_b,res_a] parameter in torch.channels_last memory format.
+ * Linear layers keep the PyTorch layout: weight [out][in], bias [out].  A NULL first-layer
+ * weight disables that head (no_dx / no_ds / no_dr / no_do / no_dshs / feat_head=False). */
+#define S3G_MAX_LEVELS 8
+typedef struct s3g_deform_net {
+    int num_levels;                        /* len(multires) */
+    int feat_dim;                          /* output_coordinate_dim, must be 32 */
+    int width;                             /* net_width, must be 64 */
+    int reso[S3G_MAX_LEVELS][4];           /* per level: resolution of x, y, z, t */
+    const float* planes[S3G_MAX_LEVELS][6];/* (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) */
+    float aabb[6];                         /* aabb[0] (max corner) then aabb[1] (min corner), hexplane.py:152-157 */
+    const float *w_feat, *b_feat;          /* feature_out.0: [64][32*L] */
+    const float *w_pos1, *b_pos1, *w_pos2, *b_pos2;      /* pos_deform.{1,3}:       [64][64], [3][64]  */
+    const float *w_scl1, *b_scl1, *w_scl2, *b_scl2;      /* scales_deform.{1,3}:    [64][64], [3][64]  */
+    const float *w_rot1, *b_rot1, *w_rot2, *b_rot2;      /* rotations_deform.{1,3}: [64][64], [4][64]  */
+    const float *w_opa1, *b_opa1, *w_opa2, *b_opa2;      /* opacity_deform.{1,3}:   [64][64], [1][64]  */
+    const float *w_shs1, *b_shs1, *w_shs2, *b_shs2;      /* shs_deform.{1,3}:       [64][64], [48][64] */
+    const float *w_dino0, *b_dino0, *w_dino2, *b_dino2, *w_dino4, *b_dino4;   /* dino_head.{0,2,4} */
+} s3g_deform_net;
+
+/* Same shape, writable: parameter gradients.  Plane gradients are ACCUMULATED (+=) with
+ * atomics and must be zeroed by the caller; Linear gradients are overwritten. */
+typedef struct s3g_deform_net_grads {
+    float* planes[S3G_MAX_LEVELS][6];
+    float *w_feat, *b_feat;
+    float *w_pos1, *b_pos1, *w_pos2, *b_pos2;
+    float *w_scl1, *b_scl1, *w_scl2, *b_scl2;
+    float *w_rot1, *b_rot1, *w_rot2, *b_rot2;
+    float *w_opa1, *b_opa1, *w_opa2, *b_opa2;
+    float *w_shs1, *b_shs1, *w_shs2, *b_shs2;
+    float *w_dino0, *b_dino0, *w_dino2, *b_dino2, *w_dino4, *b_dino4;
+} s3g_deform_net_grads;
+
+/* Forward.  Inputs are the RAW Gaussian parameters (pre-activation) [P,*]; `time` is the
+ * camera time in [0,1] (all Gaussians share it, gaussian_renderer/__init__.py:58).
+ * Outputs (all fully written): means3D [P,3] = xyz + dx, scales_act [P,3] = exp(scales+ds),
+ * rot_act [P,4] = normalize(rot+dr), opacity_act [P,1] = sigmoid(opacity+do),
+ * colors [P,3] = clamp_min(SH(shs+dshs, dir(xyz - campos)) + 0.5, 0) with the UNDEFORMED xyz,
+ * dx [P,3], dshs [P,16,3], feat [P,3].  Pointers of disabled heads may be NULL.
+ * campos: device float[3]; sh_degree: active degree (0..3). */
+int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                       const float* rotations, const float* opacity, const float* shs, float time,
+                       const float* campos, int sh_degree,
+                       float* means3D, float* scales_act, float* rot_act, float* opacity_act,
+                       float* colors, float* dx, float* dshs, float* feat, void* stream);
+
+/* Backward of the above.  g_* are dL/d(output) (NULL = zero).  Writes dL/d(raw inputs)
+ * [P,*] in full, overwrites the Linear gradients in `grads` and accumulates the plane
+ * gradients.  `workspace` must hold s3g_deform_workspace_bytes() bytes. */
+size_t s3g_deform_workspace_bytes(const s3g_deform_net* net);
+int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                        const float* rotations, const float* opacity, const float* shs, float time,
+                        const float* campos, int sh_degree,
+                        const float* g_means3D, const float* g_scales_act, const float* g_rot_act,
+                        const float* g_opacity_act, const float* g_colors, const float* g_dx,
+                        const float* g_dshs, const float* g_feat,
+                        float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
+                        const s3g_deform_net_grads* grads, void* workspace, void* stream);
 
 /* ---- per-stage device timing (bench.py roofline leg) ----------------------
  * When enabled, forward/backward bracket every kernel stage with cudaEvents on

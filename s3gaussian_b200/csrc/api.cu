@@ -13,6 +13,7 @@
 #include "binning.cuh"
 #include "common.cuh"
 #include "composite.cuh"
+#include "deform.cuh"
 #include "preprocess.cuh"
 #include "radix_sort.cuh"
 
@@ -429,6 +430,201 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     }
     S3G_STAGE("preprocess_backward");
     S3G_MARK(1, nullptr);
+    return S3G_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// HexPlane + decoder
+// ---------------------------------------------------------------------------
+namespace {
+int to_dnet(const s3g_deform_net* n, DNet& d) {
+    if (!n) return fail(S3G_ERR_ARG, "deform: null net");
+    if (n->feat_dim != FD) return fail(S3G_ERR_UNSUPPORTED, "deform: output_coordinate_dim must be 32");
+    if (n->width != HWID) return fail(S3G_ERR_UNSUPPORTED, "deform: net_width must be 64");
+    if (!(n->num_levels == 1 || n->num_levels == 2 || n->num_levels == 3 || n->num_levels == 4 ||
+          n->num_levels == 8))
+        return fail(S3G_ERR_UNSUPPORTED, "deform: number of HexPlane levels must be 1, 2, 3, 4 or 8");
+    d.L = n->num_levels;
+    for (int l = 0; l < d.L; ++l) {
+        for (int c = 0; c < 4; ++c) {
+            d.reso[l][c] = n->reso[l][c];
+            if (d.reso[l][c] < 2) return fail(S3G_ERR_ARG, "deform: plane resolution < 2");
+        }
+        for (int k = 0; k < 6; ++k) {
+            d.planes[l][k] = n->planes[l][k];
+            if (!d.planes[l][k]) return fail(S3G_ERR_ARG, "deform: null plane");
+        }
+    }
+    for (int c = 0; c < 3; ++c) {
+        d.aabb0[c] = n->aabb[c];
+        d.inv_span2[c] = 2.0f / (n->aabb[3 + c] - n->aabb[c]);   // hexplane.py:19-20
+    }
+    if (!n->w_feat || !n->b_feat) return fail(S3G_ERR_ARG, "deform: null feature_out");
+    d.w_feat = n->w_feat; d.b_feat = n->b_feat;
+    d.pos = {n->w_pos1, n->b_pos1, n->w_pos2, n->b_pos2};
+    d.scl = {n->w_scl1, n->b_scl1, n->w_scl2, n->b_scl2};
+    d.rot = {n->w_rot1, n->b_rot1, n->w_rot2, n->b_rot2};
+    d.opa = {n->w_opa1, n->b_opa1, n->w_opa2, n->b_opa2};
+    d.shs = {n->w_shs1, n->b_shs1, n->w_shs2, n->b_shs2};
+    d.w_d0 = n->w_dino0; d.b_d0 = n->b_dino0; d.w_d2 = n->w_dino2; d.b_d2 = n->b_dino2;
+    d.w_d4 = n->w_dino4; d.b_d4 = n->b_dino4;
+    const Head2* hs[5] = {&d.pos, &d.scl, &d.rot, &d.opa, &d.shs};
+    for (const Head2* h : hs)
+        if (h->w1 && !(h->b1 && h->w2 && h->b2)) return fail(S3G_ERR_ARG, "deform: incomplete head");
+    if (d.w_d0 && !(d.b_d0 && d.w_d2 && d.b_d2 && d.w_d4 && d.b_d4))
+        return fail(S3G_ERR_ARG, "deform: incomplete dino head");
+    return S3G_OK;
+}
+int deform_grid(int ntiles) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int g = 2 * sms;
+    return ntiles < g ? ntiles : g;
+}
+}  // namespace
+
+extern "C" {
+
+int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                       const float* rotations, const float* opacity, const float* shs, float time,
+                       const float* campos, int sh_degree, float* means3D, float* scales_act,
+                       float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
+                       float* feat, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
+    if (P == 0) return S3G_OK;
+    DeformFwdArgs a;
+    int rc = to_dnet(net, a.net);
+    if (rc != S3G_OK) return rc;
+    if (!xyz || !scales || !rotations || !opacity || !shs || !campos)
+        return fail(S3G_ERR_ARG, "deform_forward: null input");
+    if (!means3D || !scales_act || !rot_act || !opacity_act || !colors)
+        return fail(S3G_ERR_ARG, "deform_forward: null output");
+    if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_forward: sh_degree must be 0..3");
+    a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
+    a.campos = campos; a.time = time; a.sh_degree = sh_degree;
+    a.o_means = means3D; a.o_scales = scales_act; a.o_rot = rot_act; a.o_opacity = opacity_act;
+    a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat;
+    const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
+    const int ntiles = (P + DT - 1) / DT;
+    if (a.net.L == 4) {
+        S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
+        deform_forward_kernel<4><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
+    } else {
+        S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
+        deform_forward_kernel<0><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
+    }
+    S3G_CUDA(cudaGetLastError(), "deform_forward launch");
+    return S3G_OK;
+}
+
+
+namespace {
+// layout of one CTA's partial-gradient buffer
+int make_offsets(const DNet& d, GradOff& o) {
+    int t = 0;
+    auto take = [&](int n) { int r = t; t += (n + 3) & ~3; return r; };
+    auto head = [&](const Head2& h, int k, int (&dst)[4]) {
+        if (h.w1) { dst[0] = take(64 * 64); dst[1] = take(64); dst[2] = take(k * 64); dst[3] = take(k); }
+        else { dst[0] = dst[1] = dst[2] = dst[3] = -1; }
+    };
+    o.w_feat = take(64 * FD * d.L); o.b_feat = take(64);
+    head(d.pos, 3, o.pos); head(d.scl, 3, o.scl); head(d.rot, 4, o.rot); head(d.opa, 1, o.opa); head(d.shs, 48, o.shs);
+    if (d.w_d0) { o.d0w = take(4096); o.d0b = take(64); o.d2w = take(4096); o.d2b = take(64); o.d4w = take(192); o.d4b = take(3); }
+    else { o.d0w = o.d0b = o.d2w = o.d2b = o.d4w = o.d4b = -1; }
+    o.total = t;
+    return t;
+}
+int bwd_grid(int ntiles) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return ntiles < sms ? ntiles : sms;
+}
+constexpr int kMaxBwdGrid = 256;
+}  // namespace
+
+size_t s3g_deform_workspace_bytes(const s3g_deform_net* net) {
+    DNet d;
+    if (to_dnet(net, d) != S3G_OK) return 0;
+    GradOff o;
+    make_offsets(d, o);
+    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 256;
+}
+
+int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                        const float* rotations, const float* opacity, const float* shs, float time,
+                        const float* campos, int sh_degree, const float* g_means3D,
+                        const float* g_scales_act, const float* g_rot_act, const float* g_opacity_act,
+                        const float* g_colors, const float* g_dx, const float* g_dshs, const float* g_feat,
+                        float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
+                        const s3g_deform_net_grads* grads, void* workspace, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P < 0) return fail(S3G_ERR_ARG, "deform_backward: P < 0");
+    DeformBwdArgs a;
+    int rc = to_dnet(net, a.net);
+    if (rc != S3G_OK) return rc;
+    if (!grads || !workspace) return fail(S3G_ERR_ARG, "deform_backward: null grads/workspace");
+    if (P > 0 && (!xyz || !scales || !rotations || !opacity || !shs || !campos))
+        return fail(S3G_ERR_ARG, "deform_backward: null input");
+    if (P > 0 && (!d_xyz || !d_scales || !d_rotations || !d_opacity || !d_shs))
+        return fail(S3G_ERR_ARG, "deform_backward: null output");
+    if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_backward: sh_degree must be 0..3");
+    const DNet& d = a.net;
+    a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
+    a.campos = campos; a.time = time; a.sh_degree = sh_degree;
+    a.g_means = g_means3D; a.g_scales = g_scales_act; a.g_rot = g_rot_act; a.g_opacity = g_opacity_act;
+    a.g_colors = g_colors; a.g_dx = g_dx; a.g_dshs = g_dshs; a.g_feat = g_feat;
+    a.d_xyz = d_xyz; a.d_scales = d_scales; a.d_rot = d_rotations; a.d_opacity = d_opacity; a.d_shs = d_shs;
+    for (int l = 0; l < d.L; ++l)
+        for (int k = 0; k < 6; ++k) {
+            a.gplanes[l][k] = grads->planes[l][k];
+            if (!a.gplanes[l][k]) return fail(S3G_ERR_ARG, "deform_backward: null plane gradient");
+        }
+    make_offsets(d, a.off);
+    a.partial = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const int ntiles = (P + DT - 1) / DT;
+    int grid = bwd_grid(ntiles);
+    if (grid > kMaxBwdGrid) grid = kMaxBwdGrid;
+    // destination table of the reduction
+    ReduceArgs r;
+    r.nseg = 0; r.partial = a.partial; r.stride = a.off.total; r.nparts = grid > 0 ? grid : 0;
+    auto seg = [&](float* dst, int off, int count) -> bool {
+        if (off < 0) return true;
+        if (!dst) return false;
+        r.seg[r.nseg++] = ReduceSeg{dst, off, count};
+        return true;
+    };
+    bool ok = seg(grads->w_feat, a.off.w_feat, 64 * FD * d.L) && seg(grads->b_feat, a.off.b_feat, 64);
+    auto hseg = [&](const int (&o)[4], float* w1, float* b1, float* w2, float* b2, int k) {
+        return seg(w1, o[0], 4096) && seg(b1, o[1], 64) && seg(w2, o[2], k * 64) && seg(b2, o[3], k);
+    };
+    ok = ok && hseg(a.off.pos, grads->w_pos1, grads->b_pos1, grads->w_pos2, grads->b_pos2, 3);
+    ok = ok && hseg(a.off.scl, grads->w_scl1, grads->b_scl1, grads->w_scl2, grads->b_scl2, 3);
+    ok = ok && hseg(a.off.rot, grads->w_rot1, grads->b_rot1, grads->w_rot2, grads->b_rot2, 4);
+    ok = ok && hseg(a.off.opa, grads->w_opa1, grads->b_opa1, grads->w_opa2, grads->b_opa2, 1);
+    ok = ok && hseg(a.off.shs, grads->w_shs1, grads->b_shs1, grads->w_shs2, grads->b_shs2, 48);
+    ok = ok && seg(grads->w_dino0, a.off.d0w, 4096) && seg(grads->b_dino0, a.off.d0b, 64) &&
+         seg(grads->w_dino2, a.off.d2w, 4096) && seg(grads->b_dino2, a.off.d2b, 64) &&
+         seg(grads->w_dino4, a.off.d4w, 192) && seg(grads->b_dino4, a.off.d4b, 3);
+    if (!ok) return fail(S3G_ERR_ARG, "deform_backward: null Linear gradient for an enabled layer");
+    if (P > 0) {
+        const size_t smem = DeformBwdSmem::floats(d.L) * sizeof(float);
+        if (smem > 227 * 1024) return fail(S3G_ERR_UNSUPPORTED, "deform_backward: too many levels for shared memory");
+        if (d.L == 4) {
+            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
+            deform_backward_kernel<4><<<grid, DTHREADS, smem, stream>>>(a);
+        } else {
+            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
+            deform_backward_kernel<0><<<grid, DTHREADS, smem, stream>>>(a);
+        }
+        S3G_CUDA(cudaGetLastError(), "deform_backward launch");
+    }
+    deform_reduce_kernel<<<r.nseg, 256, 0, stream>>>(r);
+    S3G_CUDA(cudaGetLastError(), "deform_reduce launch");
     return S3G_OK;
 }
 

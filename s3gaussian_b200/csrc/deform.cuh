@@ -1,0 +1,946 @@
+// deform.cuh - HexPlane sample + multi-head deformation decoder + render() front-end,
+// fused, forward and backward, for sm_100a.
+//
+// Replaces ~150 PyTorch launches per render (24 F.grid_sample, 14 Linear/ReLU, poc_fre,
+// exp/normalize/sigmoid, eval_sh; scene/hexplane.py:73-106, scene/deformation.py:78-166,
+// gaussian_renderer/__init__.py:99-117) with one kernel each way:
+//
+//   tile of 64 Gaussians per CTA iteration (persistent grid)
+//   1. sample   one warp per Gaussian, lane = feature channel: each bilinear tap of the
+//               channels-last planes is ONE coalesced 128-byte load; the six plane
+//               samples of a level are multiplied in registers -> 32L features in smem
+//   2. decode   the dense layers run on the tensor cores as 3xTF32 (hi*hi + hi*lo + lo*hi,
+//               fp32 accumulate): 1e-4-relative parity with PyTorch fp32 rules out plain
+//               TF32/BF16 (~1e-3).  Activations never leave shared memory.
+//   3. finish   xyz+dx, exp/normalize/sigmoid, SH->RGB with the undeformed view direction,
+//               coalesced stores of the eight outputs.
+//
+// Backward recomputes 1-2 per tile (no [P,64] activations are ever stored), back-propagates
+// through the heads with the same MMA tiles, accumulates the Linear gradients in per-CTA
+// partial buffers (reduced by a second tiny kernel) and scatters plane gradients with
+// 128-byte-wide REDs.
+#pragma once
+#include "../../include/s3g_b200.h"
+#include "common.cuh"
+
+namespace s3g {
+
+constexpr int DT = 64;            // Gaussians per tile
+constexpr int DTHREADS = 256;
+constexpr int HWID = 64;          // hidden width (net_width)
+constexpr int HS = HWID + 4;      // smem row stride of 64-wide tiles (== 4 mod 32: conflict-free fragments)
+constexpr int FD = 32;            // features per plane
+
+struct Head2 {                    // Sequential(ReLU, Linear(64,64), ReLU, Linear(64,k))
+    const float *w1, *b1, *w2, *b2;
+};
+struct DNet {                     // device-side view of s3g_deform_net
+    int L;
+    int reso[S3G_MAX_LEVELS][4];
+    const float* planes[S3G_MAX_LEVELS][6];
+    float aabb0[3], inv_span2[3];     // p_hat = (p - aabb0) * inv_span2 - 1 ; inv_span2 = 2/(aabb1-aabb0)
+    const float *w_feat, *b_feat;
+    Head2 pos, scl, rot, opa, shs;
+    const float *w_d0, *b_d0, *w_d2, *b_d2, *w_d4, *b_d4;
+};
+
+__constant__ int kCombA[6] = {0, 0, 0, 1, 1, 2};
+__constant__ int kCombB[6] = {1, 2, 3, 2, 3, 3};
+
+// ---- 3xTF32 tensor-core tile product ----------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(d, al, bh);   // small terms first
+    mma_tf32(d, ah, bl);
+    mma_tf32(d, ah, bh);
+}
+
+// Stage a PyTorch-layout weight [N][K] (row n contiguous) into smem rows of stride K+4.
+template <int K>
+__device__ __forceinline__ void stage_weight(const float* __restrict__ Wg, int N, float* sW) {
+    constexpr int WS = K + 4;
+    for (int i = threadIdx.x; i < N * (K / 4); i += DTHREADS) {
+        const int n = i / (K / 4), k4 = i - n * (K / 4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Wg + (size_t)n * K) + k4);
+        *reinterpret_cast<float4*>(&sW[n * WS + 4 * k4]) = v;
+    }
+}
+
+// out[g][n] = act_out( sum_k act_in(in[g][k]) * W[n][k] + b[n] ),  g < 64, n < N (N = 64 or 48).
+// 8 warps: (warp & 3) picks 16 rows, (warp >> 2) picks half of the columns.
+// sIn / sOut / sW are distinct smem regions; ends with a __syncthreads().
+template <int K, int N, bool RELU_IN, bool RELU_OUT>
+__device__ __forceinline__ void tile_linear(const float* sIn, int inStride, const float* __restrict__ Wg,
+                                            const float* __restrict__ bg, float* sW, float* sOut,
+                                            int outStride) {
+    constexpr int WS = K + 4;
+    constexpr int NTW = N / 16;          // n-tiles (of 8) per warp
+    stage_weight<K>(Wg, N, sW);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = (warp & 3) * 16;
+    const int c0 = (warp >> 2) * (N / 2);
+    float acc[NTW][4];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const float* rowA = sIn + (r0 + g) * inStride + t;
+    const float* rowB = sIn + (r0 + g + 8) * inStride + t;
+#pragma unroll 4
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float a[4] = {rowA[k0], rowB[k0], rowA[k0 + 4], rowB[k0 + 4]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (RELU_IN) a[i] = fmaxf(a[i], 0.f);
+            split_tf32(a[i], ah[i], al[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const float* wr = sW + (c0 + 8 * j + g) * WS + k0 + t;
+            uint32_t bh[2], bl[2];
+            split_tf32(wr[0], bh[0], bl[0]);
+            split_tf32(wr[4], bh[1], bl[1]);
+            mma3(acc[j], ah, al, bh, bl);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+        const int col = c0 + 8 * j + 2 * t;
+        const float b0 = __ldg(bg + col), b1 = __ldg(bg + col + 1);
+        float v0 = acc[j][0] + b0, v1 = acc[j][1] + b1, v2 = acc[j][2] + b0, v3 = acc[j][3] + b1;
+        if (RELU_OUT) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        sOut[(r0 + g) * outStride + col] = v0;
+        sOut[(r0 + g) * outStride + col + 1] = v1;
+        sOut[(r0 + g + 8) * outStride + col] = v2;
+        sOut[(r0 + g + 8) * outStride + col + 1] = v3;
+    }
+    __syncthreads();
+}
+
+// Tiny output layers (k <= 4): out[g][o] = sum_j in[g][j] * W[o][j] + b[o]; thread = (g, o).
+__device__ __forceinline__ void tile_small_out(const float* sIn, int inStride, const float* __restrict__ Wg,
+                                               const float* __restrict__ bg, int k, float* sOut,
+                                               int outStride, int outCol) {
+    const int g = threadIdx.x >> 2, o = threadIdx.x & 3;
+    if (o < k) {
+        const float* in = sIn + g * inStride;
+        const float* w = Wg + o * HWID;
+        float s = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < HWID; ++j) s = fmaf(in[j], __ldg(w + j), s);
+        sOut[g * outStride + outCol + o] = s + __ldg(bg + o);
+    }
+}
+
+// ---- HexPlane sampling -------------------------------------------------------
+struct Tap {       // one bilinear footprint (torch grid_sample, align_corners=True, border padding)
+    int o00, o01, o10, o11;      // texel offsets (in texels), -1 = out of range (weight contributes 0)
+    float w00, w01, w10, w11;
+    float gx, gy;                // d(ix)/d(p_hat) chain factors incl. the border-clamp mask
+    float fx, fy;                // fractional parts
+};
+__device__ __forceinline__ Tap make_tap(float x, float y, int W, int H) {
+    Tap t;
+    float ix = ((x + 1.f) * 0.5f) * (float)(W - 1);
+    float iy = ((y + 1.f) * 0.5f) * (float)(H - 1);
+    // clip_coordinates: gradient is zero outside [0, size-1]
+    t.gx = (ix <= 0.f || ix >= (float)(W - 1)) ? 0.f : 0.5f * (float)(W - 1);
+    t.gy = (iy <= 0.f || iy >= (float)(H - 1)) ? 0.f : 0.5f * (float)(H - 1);
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float fx = ix - x0f, fy = iy - y0f;
+    t.fx = fx; t.fy = fy;
+    t.w00 = (1.f - fx) * (1.f - fy);
+    t.w01 = fx * (1.f - fy);
+    t.w10 = (1.f - fx) * fy;
+    t.w11 = fx * fy;
+    const bool xin = x0 + 1 <= W - 1, yin = y0 + 1 <= H - 1;
+    t.o00 = y0 * W + x0;
+    t.o01 = xin ? y0 * W + x0 + 1 : -1;
+    t.o10 = yin ? (y0 + 1) * W + x0 : -1;
+    t.o11 = (xin && yin) ? (y0 + 1) * W + x0 + 1 : -1;
+    return t;
+}
+__device__ __forceinline__ float tap_fetch(const float* __restrict__ plane, int off, int lane) {
+    return off >= 0 ? __ldg(plane + (size_t)off * FD + lane) : 0.f;
+}
+
+// features of one Gaussian (this lane's channel) for all levels -> sFrow[32*l + lane].
+// With a compile-time level count every tap address is computed first and all
+// 24*L 128-byte loads are in flight together (the phase is latency-bound otherwise).
+template <int LT>
+__device__ __forceinline__ void sample_gaussian(const DNet& n, const float ph[4], int lane, float* sFrow) {
+    if constexpr (LT > 0 && (LT % 2) == 0) {
+        // two levels (48 loads) in flight at a time: 96 live texel registers spill
+#pragma unroll 1
+        for (int l0 = 0; l0 < LT; l0 += 2) {
+            float v[2][6][4];
+            float fx[2][6], fy[2][6];
+#pragma unroll
+            for (int dl = 0; dl < 2; ++dl) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int a = kCombA[k], b = kCombB[k];
+                    const Tap t = make_tap(ph[a], ph[b], n.reso[l0 + dl][a], n.reso[l0 + dl][b]);
+                    const float* pl = n.planes[l0 + dl][k];
+                    v[dl][k][0] = tap_fetch(pl, t.o00, lane);
+                    v[dl][k][1] = tap_fetch(pl, t.o01, lane);
+                    v[dl][k][2] = tap_fetch(pl, t.o10, lane);
+                    v[dl][k][3] = tap_fetch(pl, t.o11, lane);
+                    fx[dl][k] = t.fx; fy[dl][k] = t.fy;
+                }
+            }
+#pragma unroll
+            for (int dl = 0; dl < 2; ++dl) {
+                float f = 1.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float x = fx[dl][k], y = fy[dl][k];
+                    const float s = (1.f - x) * (1.f - y) * v[dl][k][0] + x * (1.f - y) * v[dl][k][1] +
+                                    (1.f - x) * y * v[dl][k][2] + x * y * v[dl][k][3];
+                    f = (k == 0) ? s : f * s;     // interp_space = 1 * s0 * s1 * ... (hexplane.py:87-96)
+                }
+                sFrow[(l0 + dl) * FD + lane] = f;
+            }
+        }
+        return;
+    }
+    for (int l = 0; l < n.L; ++l) {
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int a = kCombA[k], b = kCombB[k];
+            const Tap t = make_tap(ph[a], ph[b], n.reso[l][a], n.reso[l][b]);
+            const float* pl = n.planes[l][k];
+            v[k] = t.w00 * tap_fetch(pl, t.o00, lane) + t.w01 * tap_fetch(pl, t.o01, lane) +
+                   t.w10 * tap_fetch(pl, t.o10, lane) + t.w11 * tap_fetch(pl, t.o11, lane);
+        }
+        sFrow[l * FD + lane] = ((((v[0] * v[1]) * v[2]) * v[3]) * v[4]) * v[5];
+    }
+}
+
+// SH basis (utils/sh_utils.py:57-112) for unit direction (x,y,z); returns count
+__device__ __forceinline__ int sh_basis16(int deg, float x, float y, float z, float* b) {
+    b[0] = 0.28209479177387814f;
+    if (deg < 1) return 1;
+    const float C1 = 0.4886025119029199f;
+    b[1] = -C1 * y; b[2] = C1 * z; b[3] = -C1 * x;
+    if (deg < 2) return 4;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = 1.0925484305920792f * xy; b[5] = -1.0925484305920792f * yz;
+    b[6] = 0.31539156525252005f * (2.f * zz - xx - yy);
+    b[7] = -1.0925484305920792f * xz; b[8] = 0.5462742152960396f * (xx - yy);
+    if (deg < 3) return 9;
+    b[9] = -0.5900435899266435f * y * (3.f * xx - yy);
+    b[10] = 2.890611442640554f * xy * z;
+    b[11] = -0.4570457994644658f * y * (4.f * zz - xx - yy);
+    b[12] = 0.3731763325901154f * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    b[13] = -0.4570457994644658f * x * (4.f * zz - xx - yy);
+    b[14] = 1.445305721320277f * z * (xx - yy);
+    b[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
+    return 16;
+}
+
+struct DeformFwdArgs {
+    DNet net;
+    int P;
+    const float *xyz, *scales, *rot, *opacity, *shs, *campos;
+    float time;
+    int sh_degree;
+    float *o_means, *o_scales, *o_rot, *o_opacity, *o_colors, *o_dx, *o_dshs, *o_feat;
+};
+
+// smem carve (floats).  FS = 32L+4.
+struct DeformSmem {
+    float *F, *H, *A, *B, *W, *S, *Dsh, *X;
+    __device__ DeformSmem(float* base, int L) {
+        const int FS = FD * L + 4;
+        F = base;                         // [64][FS]   features, dead after h; A and B alias it
+        A = F;                            // [64][HS]
+        B = F + DT * HS;                  // [64][HS]   (needs 2*HS <= FS, i.e. L >= 4, else separate: see host sizing)
+        H = base + DT * (FS > 2 * HS ? FS : 2 * HS);      // [64][HS]
+        W = H + DT * HS;                  // [64][max(FS,HS)] weight staging
+        S = W + HWID * (FS > HS ? FS : HS);               // [64][16] small head outputs
+        Dsh = S + DT * 16;                // [64][52] dshs / shs_final
+        X = Dsh + DT * 52;                // [64][4] xyz of the tile
+    }
+    __host__ __device__ static size_t floats(int L) {
+        const int FS = FD * L + 4;
+        return (size_t)DT * (FS > 2 * HS ? FS : 2 * HS) + DT * HS + HWID * (FS > HS ? FS : HS) + DT * 16 + DT * 52 + DT * 4;
+    }
+};
+// columns of the small-output tile S
+constexpr int S_DX = 0, S_DS = 3, S_DR = 6, S_DO = 10, S_FEAT = 11;
+
+template <int LT>   // LT = 4: compile-time level count (K of the first layer = 128); 0: generic via K=32*L switch
+__global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdArgs a) {
+    extern __shared__ __align__(16) float s_dyn[];
+    const DNet& n = a.net;
+    const int L = n.L;
+    const int FS = FD * L + 4;
+    DeformSmem sm(s_dyn, L);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntiles = (a.P + DT - 1) / DT;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int g0 = tile * DT;
+        // ---- tile inputs ---------------------------------------------------
+        if (tid < DT * 3) {
+            const int g = tid / 3, c = tid - 3 * g;
+            sm.X[g * 4 + c] = (g0 + g < a.P) ? a.xyz[(size_t)(g0 + g) * 3 + c] : 0.f;
+        }
+        __syncthreads();
+        // ---- 1. HexPlane sampling: warp w takes Gaussians w, w+8, ... --------
+        for (int g = warp; g < DT; g += DTHREADS / 32) {
+            float ph[4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
+            ph[3] = a.time;
+            sample_gaussian<LT>(n, ph, lane, sm.F + g * FS);
+        }
+        __syncthreads();
+        // ---- 2. decoder ------------------------------------------------------
+        // h = feature_out(f)
+        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        // zero the small outputs (disabled heads contribute 0)
+        for (int i = tid; i < DT * 16; i += DTHREADS) sm.S[i] = 0.f;
+        __syncthreads();
+        if (n.pos.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.pos.w1, n.pos.b1, sm.W, sm.A, HS);
+            tile_small_out(sm.A, HS, n.pos.w2, n.pos.b2, 3, sm.S, 16, S_DX);
+        }
+        if (n.scl.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.scl.w1, n.scl.b1, sm.W, sm.B, HS);
+            tile_small_out(sm.B, HS, n.scl.w2, n.scl.b2, 3, sm.S, 16, S_DS);
+        }
+        __syncthreads();
+        if (n.rot.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.rot.w1, n.rot.b1, sm.W, sm.A, HS);
+            tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.S, 16, S_DR);
+        }
+        if (n.opa.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.opa.w1, n.opa.b1, sm.W, sm.B, HS);
+            tile_small_out(sm.B, HS, n.opa.w2, n.opa.b2, 1, sm.S, 16, S_DO);
+        }
+        __syncthreads();
+        if (n.shs.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.shs.w1, n.shs.b1, sm.W, sm.A, HS);
+            tile_linear<64, 48, false, false>(sm.A, HS, n.shs.w2, n.shs.b2, sm.W, sm.Dsh, 52);
+        } else {
+            for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dsh[i] = 0.f;
+            __syncthreads();
+        }
+        if (n.w_d0) {   // dino head: Linear, ReLU, Linear, ReLU, Linear - no leading ReLU (deformation.py:70-76)
+            tile_linear<64, 64, false, true>(sm.H, HS, n.w_d0, n.b_d0, sm.W, sm.A, HS);
+            tile_linear<64, 64, false, true>(sm.A, HS, n.w_d2, n.b_d2, sm.W, sm.B, HS);
+            tile_small_out(sm.B, HS, n.w_d4, n.b_d4, 3, sm.S, 16, S_FEAT);
+        }
+        __syncthreads();
+        // ---- 3. finish ---------------------------------------------------------
+        // dshs out (coalesced) and shs_final = shs + dshs kept in smem
+        for (int e = tid; e < DT * 48; e += DTHREADS) {
+            const int g = e / 48, j = e - 48 * g;
+            if (g0 + g < a.P) {
+                const float d = sm.Dsh[g * 52 + j];
+                if (a.o_dshs) a.o_dshs[(size_t)(g0 + g) * 48 + j] = d;
+                sm.Dsh[g * 52 + j] = a.shs[(size_t)(g0 + g) * 48 + j] + d;
+            }
+        }
+        __syncthreads();
+        {
+            const int g = tid >> 2, c = tid & 3;
+            const int gi = g0 + g;
+            if (gi < a.P) {
+                const float* S = sm.S + g * 16;
+                if (c < 3) {
+                    const float p = sm.X[g * 4 + c];
+                    const float d = S[S_DX + c];
+                    a.o_means[(size_t)gi * 3 + c] = p + d;                                  // pts*mask + dx, mask == 1
+                    if (a.o_dx) a.o_dx[(size_t)gi * 3 + c] = d;
+                    if (a.o_feat) a.o_feat[(size_t)gi * 3 + c] = S[S_FEAT + c];
+                    a.o_scales[(size_t)gi * 3 + c] = expf(a.scales[(size_t)gi * 3 + c] + S[S_DS + c]);
+                    // SH -> RGB with the UNDEFORMED position (gaussian_renderer/__init__.py:110)
+                    float dx_ = sm.X[g * 4 + 0] - a.campos[0], dy_ = sm.X[g * 4 + 1] - a.campos[1],
+                          dz_ = sm.X[g * 4 + 2] - a.campos[2];
+                    const float inv = 1.0f / sqrtf(dx_ * dx_ + dy_ * dy_ + dz_ * dz_);
+                    float bs[16];
+                    const int nb = sh_basis16(a.sh_degree, dx_ * inv, dy_ * inv, dz_ * inv, bs);
+                    float r = 0.f;
+                    for (int k = 0; k < nb; ++k) r = fmaf(bs[k], sm.Dsh[g * 52 + 3 * k + c], r);
+                    a.o_colors[(size_t)gi * 3 + c] = fmaxf(r + 0.5f, 0.0f);
+                } else {
+                    // rotation (normalize, eps 1e-12) and opacity (sigmoid)
+                    float q[4], nn = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        q[i] = a.rot[(size_t)gi * 4 + i] + S[S_DR + i];
+                        nn += q[i] * q[i];
+                    }
+                    const float invn = 1.0f / fmaxf(sqrtf(nn), 1e-12f);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a.o_rot[(size_t)gi * 4 + i] = q[i] * invn;
+                    const float o = a.opacity[gi] + S[S_DO];
+                    a.o_opacity[gi] = 1.0f / (1.0f + expf(-o));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// =============================================================================
+// Backward
+// =============================================================================
+
+// out[g][k] (op)= ( sum_n in[g][n] * W[n][k] ) (* [mask[g][k] > 0]),  W is the PyTorch [N][K] weight,
+// i.e. the transposed product used to push deltas back through a Linear.
+enum { TL_ASSIGN = 0, TL_ASSIGN_MASK = 1, TL_ACCUM = 2, TL_ACCUM_MASK = 3 };
+template <int K, int N, int MODE>
+__device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, const float* __restrict__ Wg,
+                                              float* sW, float* sOut, int outStride, const float* sMask,
+                                              int maskStride) {
+    constexpr int WS = K + 4;
+    constexpr int NTW = K / 16;          // output n-tiles (of 8) per warp
+    stage_weight<K>(Wg, N, sW);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = (warp & 3) * 16;
+    const int c0 = (warp >> 2) * (K / 2);
+    float acc[NTW][4];
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const float* rowA = sIn + (r0 + g) * inStride + t;
+    const float* rowB = sIn + (r0 + g + 8) * inStride + t;
+#pragma unroll 2
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        const float a[4] = {rowA[n0], rowB[n0], rowA[n0 + 4], rowB[n0 + 4]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+        for (int j = 0; j < NTW; ++j) {
+            const float* wr = sW + (n0 + t) * WS + c0 + 8 * j + g;
+            uint32_t bh[2], bl[2];
+            split_tf32(wr[0], bh[0], bl[0]);
+            split_tf32(wr[4 * WS], bh[1], bl[1]);
+            mma3(acc[j], ah, al, bh, bl);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+        const int col = c0 + 8 * j + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = r0 + g + 8 * h;
+            float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
+            if (MODE == TL_ASSIGN_MASK || MODE == TL_ACCUM_MASK) {
+                if (!(sMask[row * maskStride + col] > 0.f)) v0 = 0.f;
+                if (!(sMask[row * maskStride + col + 1] > 0.f)) v1 = 0.f;
+            }
+            float* o = sOut + row * outStride + col;
+            if (MODE == TL_ACCUM || MODE == TL_ACCUM_MASK) { o[0] += v0; o[1] += v1; }
+            else { o[0] = v0; o[1] = v1; }
+        }
+    }
+    __syncthreads();
+}
+
+// gW[m][n] += sum_g delta[g][m] * act(actv[g][n])   (Linear weight gradient of one tile)
+// gb[m]    += sum_g delta[g][m]
+template <int M, int NIN, bool RELU_ACT>
+__device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const float* sAct, int aStride,
+                                         float* __restrict__ gW, float* __restrict__ gb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int TN = NIN / 8;
+    constexpr int TILES = (M / 16) * TN;
+    for (int tile = warp; tile < TILES; tile += DTHREADS / 32) {
+        const int m0 = (tile / TN) * 16, n0 = (tile % TN) * 8;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int k0 = 0; k0 < DT; k0 += 8) {
+            // A[m][k] = delta[k][m]
+            const float a[4] = {sDelta[(k0 + t) * dStride + m0 + g], sDelta[(k0 + t) * dStride + m0 + g + 8],
+                                sDelta[(k0 + t + 4) * dStride + m0 + g], sDelta[(k0 + t + 4) * dStride + m0 + g + 8]};
+            float b[2] = {sAct[(k0 + t) * aStride + n0 + g], sAct[(k0 + t + 4) * aStride + n0 + g]};
+            if (RELU_ACT) { b[0] = fmaxf(b[0], 0.f); b[1] = fmaxf(b[1], 0.f); }
+            uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+            split_tf32(b[0], bh[0], bl[0]);
+            split_tf32(b[1], bh[1], bl[1]);
+            mma3(acc, ah, al, bh, bl);
+        }
+        float2* p0 = reinterpret_cast<float2*>(gW + (size_t)(m0 + g) * NIN + n0 + 2 * t);
+        float2* p1 = reinterpret_cast<float2*>(gW + (size_t)(m0 + g + 8) * NIN + n0 + 2 * t);
+        float2 v0 = *p0, v1 = *p1;
+        v0.x += acc[0]; v0.y += acc[1]; v1.x += acc[2]; v1.y += acc[3];
+        *p0 = v0; *p1 = v1;
+    }
+    if (threadIdx.x < M) {
+        float sacc = 0.f;
+        for (int k = 0; k < DT; ++k) sacc += sDelta[k * dStride + threadIdx.x];
+        gb[threadIdx.x] += sacc;
+    }
+}
+
+// small output layer (k <= 4 outputs): weight/bias gradients and delta push-back, SIMT.
+//   gW2[o][j] += sum_g dout[g][o] * act[g][j];  gb2[o] += sum_g dout[g][o]
+//   D[g][j] = (sum_o dout[g][o] * W2[o][j]) * [act[g][j] > 0]
+__device__ __forceinline__ void small_head_backward(const float* sDout, int k, const float* sAct, int aStride,
+                                                    const float* __restrict__ W2, float* __restrict__ gW2,
+                                                    float* __restrict__ gb2, float* sD, int dStride) {
+    const int tid = threadIdx.x;
+    {   // weight grads: thread -> (o, j)
+        const int o = tid >> 6, j = tid & 63;
+        if (o < k) {
+            float sacc = 0.f;
+            for (int g = 0; g < DT; ++g) sacc = fmaf(sDout[g * 4 + o], sAct[g * aStride + j], sacc);
+            gW2[o * HWID + j] += sacc;
+        }
+        if (tid < k) {
+            float sb = 0.f;
+            for (int g = 0; g < DT; ++g) sb += sDout[g * 4 + tid];
+            gb2[tid] += sb;
+        }
+    }
+    for (int e = tid; e < DT * HWID; e += DTHREADS) {
+        const int g = e >> 6, j = e & 63;
+        float v = 0.f;
+        for (int o = 0; o < k; ++o) v = fmaf(sDout[g * 4 + o], __ldg(W2 + o * HWID + j), v);
+        sD[g * dStride + j] = sAct[g * aStride + j] > 0.f ? v : 0.f;
+    }
+    __syncthreads();
+}
+
+struct GradOff {     // offsets (in floats) of every Linear gradient inside one CTA's partial buffer; -1 = disabled
+    int w_feat, b_feat;
+    int pos[4], scl[4], rot[4], opa[4], shs[4];     // w1, b1, w2, b2
+    int d0w, d0b, d2w, d2b, d4w, d4b;
+    int total;
+};
+
+struct DeformBwdArgs {
+    DNet net;
+    int P;
+    const float *xyz, *scales, *rot, *opacity, *shs, *campos;
+    float time;
+    int sh_degree;
+    const float *g_means, *g_scales, *g_rot, *g_opacity, *g_colors, *g_dx, *g_dshs, *g_feat;
+    float *d_xyz, *d_scales, *d_rot, *d_opacity, *d_shs;
+    float* gplanes[S3G_MAX_LEVELS][6];
+    float* partial;      // [gridDim.x][off.total]
+    GradOff off;
+};
+
+struct DeformBwdSmem {
+    float *X, *F, *H, *DH, *A, *B, *D1, *D2, *Dout, *W, *G;
+    __device__ DeformBwdSmem(float* base, int L) {
+        const int FS = FD * L + 4;
+        const int AB = (FS > 2 * HS ? FS : 2 * HS);
+        X = base;                      // [64][4]
+        F = X + DT * 4;                // [64][FS]
+        H = F + DT * FS;               // [64][HS]
+        DH = H + DT * HS;
+        A = DH + DT * HS;              // A and B are contiguous: DF [64][FS] aliases them at the end
+        B = A + DT * HS;
+        D1 = A + DT * AB;
+        D2 = D1 + DT * HS;
+        Dout = D2 + DT * HS;           // [64][52]
+        W = Dout + DT * 52;            // [64][max(FS,HS)]
+        G = W + HWID * (FS > HS ? FS : HS);   // [64][16] per-Gaussian scalars (small deltas)
+    }
+    __host__ __device__ static size_t floats(int L) {
+        const int FS = FD * L + 4;
+        const int AB = (FS > 2 * HS ? FS : 2 * HS);
+        return (size_t)DT * 4 + DT * FS + 2 * DT * HS + DT * AB + 2 * DT * HS + DT * 52 + HWID * (FS > HS ? FS : HS) + DT * 16;
+    }
+};
+
+__device__ __forceinline__ float ldz(const float* p, size_t i) { return p ? p[i] : 0.f; }
+
+template <int KF>   // KF = 32*L
+__device__ __forceinline__ void feat_layers_bwd(const DeformBwdSmem& sm, const DNet& n, float* part, const GradOff& off,
+                                                int FS) {
+    // dW0 += DH^T F ; db0 ; DF = DH W0  (DF aliases A|B)
+    dw_accum<64, KF, false>(sm.DH, HS, sm.F, FS, part + off.w_feat, part + off.b_feat);
+    __syncthreads();
+    tile_linear_T<KF, 64, TL_ASSIGN>(sm.DH, HS, n.w_feat, sm.W, sm.A, FS, nullptr, 0);
+}
+
+template <int LT>
+__global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdArgs a) {
+    extern __shared__ __align__(16) float s_dyn[];
+    const DNet& n = a.net;
+    const int L = n.L;
+    const int FS = FD * L + 4;
+    DeformBwdSmem sm(s_dyn, L);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntiles = (a.P + DT - 1) / DT;
+    float* part = a.partial + (size_t)blockIdx.x * a.off.total;
+    for (int i = tid; i < a.off.total; i += DTHREADS) part[i] = 0.f;
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int g0 = tile * DT;
+        if (tid < DT * 3) {
+            const int g = tid / 3, c = tid - 3 * g;
+            sm.X[g * 4 + c] = (g0 + g < a.P) ? a.xyz[(size_t)(g0 + g) * 3 + c] : 0.f;
+        }
+        for (int i = tid; i < DT * HS; i += DTHREADS) sm.DH[i] = 0.f;
+        __syncthreads();
+        // ---- recompute: features and hidden -----------------------------------
+        for (int g = warp; g < DT; g += DTHREADS / 32) {
+            float ph[4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
+            ph[3] = a.time;
+            sample_gaussian<LT>(n, ph, lane, sm.F + g * FS);
+        }
+        __syncthreads();
+        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+
+        // ---- per-Gaussian activation backward -> small deltas in G[g][0..10] ----
+        //  G: [0..2] d(dx) , [3..5] d(ds), [6..9] d(dr), [10] d(do)
+        if (tid < DT) {
+            const int g = tid, gi = g0 + g;
+            float* G = sm.G + g * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) G[i] = 0.f;
+            if (gi < a.P) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) G[c] = ldz(a.g_means, (size_t)gi * 3 + c) + ldz(a.g_dx, (size_t)gi * 3 + c);
+            }
+        }
+        __syncthreads();
+        // scales / rotation / opacity need their head outputs first (when the heads are on), so
+        // the forward of those heads is recomputed into S-like columns of G[11..15] lazily below.
+
+        // ---- pos head ------------------------------------------------------------
+        if (n.pos.w1) {
+            tile_linear<64, 64, true, true>(sm.H, HS, n.pos.w1, n.pos.b1, sm.W, sm.A, HS);
+            if (tid < DT * 4) sm.Dout[tid] = sm.G[(tid >> 2) * 16 + (tid & 3)] * ((tid & 3) < 3 ? 1.f : 0.f);
+            __syncthreads();
+            small_head_backward(sm.Dout, 3, sm.A, HS, n.pos.w2, part + a.off.pos[2], part + a.off.pos[3], sm.D1, HS);
+            dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.pos[0], part + a.off.pos[1]);
+            tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.pos.w1, sm.W, sm.DH, HS, sm.H, HS);
+        }
+        // ---- scales head: scales_act = exp(scales + ds) ---------------------------
+        {
+            const bool on = n.scl.w1 != nullptr;
+            if (on) {
+                tile_linear<64, 64, true, true>(sm.H, HS, n.scl.w1, n.scl.b1, sm.W, sm.A, HS);
+                tile_small_out(sm.A, HS, n.scl.w2, n.scl.b2, 3, sm.G, 16, 11);     // ds -> G[11..13]
+                __syncthreads();
+            }
+            if (tid < DT * 4) {
+                const int g = tid >> 2, c = tid & 3, gi = g0 + g;
+                float d = 0.f;
+                if (c < 3 && gi < a.P) {
+                    const float sfin = a.scales[(size_t)gi * 3 + c] + (on ? sm.G[g * 16 + 11 + c] : 0.f);
+                    d = ldz(a.g_scales, (size_t)gi * 3 + c) * expf(sfin);
+                    a.d_scales[(size_t)gi * 3 + c] = d;
+                }
+                sm.Dout[tid] = d;
+            }
+            __syncthreads();
+            if (on) {
+                small_head_backward(sm.Dout, 3, sm.A, HS, n.scl.w2, part + a.off.scl[2], part + a.off.scl[3], sm.D1, HS);
+                dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.scl[0], part + a.off.scl[1]);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.scl.w1, sm.W, sm.DH, HS, sm.H, HS);
+            }
+        }
+        // ---- rotation head: rot_act = normalize(rot + dr) --------------------------
+        {
+            const bool on = n.rot.w1 != nullptr;
+            if (on) {
+                tile_linear<64, 64, true, true>(sm.H, HS, n.rot.w1, n.rot.b1, sm.W, sm.A, HS);
+                tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.G, 16, 11);     // dr -> G[11..14]
+                __syncthreads();
+            }
+            if (tid < DT) {
+                const int g = tid, gi = g0 + g;
+                float dq[4] = {0.f, 0.f, 0.f, 0.f};
+                if (gi < a.P) {
+                    float q[4], gq[4], nn = 0.f, dot = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        q[i] = a.rot[(size_t)gi * 4 + i] + (on ? sm.G[g * 16 + 11 + i] : 0.f);
+                        gq[i] = ldz(a.g_rot, (size_t)gi * 4 + i);
+                        nn += q[i] * q[i];
+                    }
+                    const float nrm = sqrtf(nn);
+                    if (nrm > 1e-12f) {          // F.normalize: x / max(|x|, eps)
+                        const float inv = 1.f / nrm;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dot += q[i] * inv * gq[i];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dq[i] = (gq[i] - q[i] * inv * dot) * inv;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dq[i] = gq[i] * 1e12f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a.d_rot[(size_t)gi * 4 + i] = dq[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sm.Dout[g * 4 + i] = dq[i];
+            }
+            __syncthreads();
+            if (on) {
+                small_head_backward(sm.Dout, 4, sm.A, HS, n.rot.w2, part + a.off.rot[2], part + a.off.rot[3], sm.D1, HS);
+                dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.rot[0], part + a.off.rot[1]);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.rot.w1, sm.W, sm.DH, HS, sm.H, HS);
+            }
+        }
+        // ---- opacity head: opacity_act = sigmoid(opacity + do) ---------------------
+        {
+            const bool on = n.opa.w1 != nullptr;
+            if (on) {
+                tile_linear<64, 64, true, true>(sm.H, HS, n.opa.w1, n.opa.b1, sm.W, sm.A, HS);
+                tile_small_out(sm.A, HS, n.opa.w2, n.opa.b2, 1, sm.G, 16, 11);     // do -> G[11]
+                __syncthreads();
+            }
+            if (tid < DT * 4) {
+                const int g = tid >> 2, c = tid & 3, gi = g0 + g;
+                float d = 0.f;
+                if (c == 0 && gi < a.P) {
+                    const float o = a.opacity[gi] + (on ? sm.G[g * 16 + 11] : 0.f);
+                    const float sg = 1.0f / (1.0f + expf(-o));
+                    d = ldz(a.g_opacity, gi) * sg * (1.f - sg);
+                    a.d_opacity[gi] = d;
+                }
+                sm.Dout[tid] = d;
+            }
+            __syncthreads();
+            if (on) {
+                small_head_backward(sm.Dout, 1, sm.A, HS, n.opa.w2, part + a.off.opa[2], part + a.off.opa[3], sm.D1, HS);
+                dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.opa[0], part + a.off.opa[1]);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.opa.w1, sm.W, sm.DH, HS, sm.H, HS);
+            }
+        }
+        // ---- shs head + SH->RGB backward ---------------------------------------------
+        {
+            const bool on = n.shs.w1 != nullptr;
+            if (on) {
+                tile_linear<64, 64, true, true>(sm.H, HS, n.shs.w1, n.shs.b1, sm.W, sm.A, HS);
+                tile_linear<64, 48, false, false>(sm.A, HS, n.shs.w2, n.shs.b2, sm.W, sm.Dout, 52);   // dshs
+            } else {
+                for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dout[i] = 0.f;
+                __syncthreads();
+            }
+            // shs_final = shs + dshs (in place)
+            for (int e = tid; e < DT * 48; e += DTHREADS) {
+                const int g = e / 48, j = e - 48 * g;
+                if (g0 + g < a.P) sm.Dout[g * 52 + j] += a.shs[(size_t)(g0 + g) * 48 + j];
+            }
+            __syncthreads();
+            // per Gaussian: colour clamp mask, dL/dshs_final = basis (x) g_col, dL/d(dir) -> d_xyz part (into G[11..13])
+            if (tid < DT) {
+                const int g = tid, gi = g0 + g;
+                float dxyz[3] = {0.f, 0.f, 0.f};
+                float bs[16];
+                float gr[3] = {0.f, 0.f, 0.f};
+                int nb = 0;
+                if (gi < a.P) {
+                    const float vx = sm.X[g * 4 + 0] - a.campos[0], vy = sm.X[g * 4 + 1] - a.campos[1],
+                                vz = sm.X[g * 4 + 2] - a.campos[2];
+                    const float s2 = vx * vx + vy * vy + vz * vz;
+                    const float inv = 1.0f / sqrtf(s2);
+                    const float x = vx * inv, y = vy * inv, z = vz * inv;
+                    nb = sh_basis16(a.sh_degree, x, y, z, bs);
+                    float* sf = sm.Dout + g * 52;
+                    float ddir[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float r = 0.f;
+                        for (int k = 0; k < nb; ++k) r = fmaf(bs[k], sf[3 * k + c], r);
+                        gr[c] = (r + 0.5f > 0.0f) ? ldz(a.g_colors, (size_t)gi * 3 + c) : 0.f;   // clamp_min(.,0)
+                    }
+                    if (a.sh_degree > 0) {
+                        const float C1 = 0.4886025119029199f;
+                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+#define SHF(i) sf[3 * (i) + c]
+                            float dx_ = -C1 * SHF(3), dy_ = -C1 * SHF(1), dz_ = C1 * SHF(2);
+                            if (a.sh_degree > 1) {
+                                dx_ += 1.0925484305920792f * y * SHF(4) + 0.31539156525252005f * -2.f * x * SHF(6) +
+                                       -1.0925484305920792f * z * SHF(7) + 0.5462742152960396f * 2.f * x * SHF(8);
+                                dy_ += 1.0925484305920792f * x * SHF(4) + -1.0925484305920792f * z * SHF(5) +
+                                       0.31539156525252005f * -2.f * y * SHF(6) + 0.5462742152960396f * -2.f * y * SHF(8);
+                                dz_ += -1.0925484305920792f * y * SHF(5) + 0.31539156525252005f * 4.f * z * SHF(6) +
+                                       -1.0925484305920792f * x * SHF(7);
+                            }
+                            if (a.sh_degree > 2) {
+                                dx_ += -0.5900435899266435f * SHF(9) * 6.f * xy + 2.890611442640554f * SHF(10) * yz +
+                                       -0.4570457994644658f * SHF(11) * -2.f * xy + 0.3731763325901154f * SHF(12) * -6.f * xz +
+                                       -0.4570457994644658f * SHF(13) * (-3.f * xx + 4.f * zz - yy) +
+                                       1.445305721320277f * SHF(14) * 2.f * xz + -0.5900435899266435f * SHF(15) * 3.f * (xx - yy);
+                                dy_ += -0.5900435899266435f * SHF(9) * 3.f * (xx - yy) + 2.890611442640554f * SHF(10) * xz +
+                                       -0.4570457994644658f * SHF(11) * (-3.f * yy + 4.f * zz - xx) +
+                                       0.3731763325901154f * SHF(12) * -6.f * yz + -0.4570457994644658f * SHF(13) * -2.f * xy +
+                                       1.445305721320277f * SHF(14) * -2.f * yz + -0.5900435899266435f * SHF(15) * -6.f * xy;
+                                dz_ += 2.890611442640554f * SHF(10) * xy + -0.4570457994644658f * SHF(11) * 8.f * yz +
+                                       0.3731763325901154f * SHF(12) * 3.f * (2.f * zz - xx - yy) +
+                                       -0.4570457994644658f * SHF(13) * 8.f * xz + 1.445305721320277f * SHF(14) * (xx - yy);
+                            }
+#undef SHF
+                            ddir[0] += dx_ * gr[c]; ddir[1] += dy_ * gr[c]; ddir[2] += dz_ * gr[c];
+                        }
+                        // through dir = v / |v|
+                        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
+                        const float dot = vx * ddir[0] + vy * ddir[1] + vz * ddir[2];
+                        dxyz[0] = (s2 * ddir[0] - vx * dot) * inv32;
+                        dxyz[1] = (s2 * ddir[1] - vy * dot) * inv32;
+                        dxyz[2] = (s2 * ddir[2] - vz * dot) * inv32;
+                    }
+                }
+                sm.G[g * 16 + 11] = dxyz[0]; sm.G[g * 16 + 12] = dxyz[1]; sm.G[g * 16 + 13] = dxyz[2];
+                // overwrite the row with dL/dshs_final
+                float* sf = sm.Dout + g * 52;
+                for (int k = 0; k < 16; ++k) {
+                    const float b = k < nb ? bs[k] : 0.f;
+                    sf[3 * k + 0] = b * gr[0]; sf[3 * k + 1] = b * gr[1]; sf[3 * k + 2] = b * gr[2];
+                }
+            }
+            __syncthreads();
+            // d_shs (param) = dL/dshs_final ; delta of the head output = that + g_dshs
+            for (int e = tid; e < DT * 48; e += DTHREADS) {
+                const int g = e / 48, j = e - 48 * g;
+                if (g0 + g < a.P) {
+                    const float v = sm.Dout[g * 52 + j];
+                    a.d_shs[(size_t)(g0 + g) * 48 + j] = v;
+                    sm.Dout[g * 52 + j] = v + ldz(a.g_dshs, (size_t)(g0 + g) * 48 + j);
+                } else {
+                    sm.Dout[g * 52 + j] = 0.f;
+                }
+            }
+            __syncthreads();
+            if (on) {
+                dw_accum<48, 64, false>(sm.Dout, 52, sm.A, HS, part + a.off.shs[2], part + a.off.shs[3]);
+                tile_linear_T<64, 48, TL_ASSIGN_MASK>(sm.Dout, 52, n.shs.w2, sm.W, sm.D1, HS, sm.A, HS);
+                dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.shs[0], part + a.off.shs[1]);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.shs.w1, sm.W, sm.DH, HS, sm.H, HS);
+            }
+        }
+        // ---- dino head ------------------------------------------------------------------
+        if (n.w_d0) {
+            tile_linear<64, 64, false, true>(sm.H, HS, n.w_d0, n.b_d0, sm.W, sm.A, HS);
+            tile_linear<64, 64, false, true>(sm.A, HS, n.w_d2, n.b_d2, sm.W, sm.B, HS);
+            if (tid < DT * 4) {
+                const int g = tid >> 2, c = tid & 3, gi = g0 + g;
+                sm.Dout[tid] = (c < 3 && gi < a.P) ? ldz(a.g_feat, (size_t)gi * 3 + c) : 0.f;
+            }
+            __syncthreads();
+            small_head_backward(sm.Dout, 3, sm.B, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS);
+            dw_accum<64, 64, false>(sm.D2, HS, sm.A, HS, part + a.off.d2w, part + a.off.d2b);
+            tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, n.w_d2, sm.W, sm.D1, HS, sm.A, HS);
+            dw_accum<64, 64, false>(sm.D1, HS, sm.H, HS, part + a.off.d0w, part + a.off.d0b);
+            tile_linear_T<64, 64, TL_ACCUM>(sm.D1, HS, n.w_d0, sm.W, sm.DH, HS, nullptr, 0);
+        }
+        __syncthreads();
+        // ---- feature layer ---------------------------------------------------------------
+        if (LT == 4 || L == 4) feat_layers_bwd<128>(sm, n, part, a.off, FS);
+        else if (L == 1) feat_layers_bwd<32>(sm, n, part, a.off, FS);
+        else if (L == 2) feat_layers_bwd<64>(sm, n, part, a.off, FS);
+        else if (L == 3) feat_layers_bwd<96>(sm, n, part, a.off, FS);
+        else if (L == 8) feat_layers_bwd<256>(sm, n, part, a.off, FS);
+        // DF now lives in sm.A with row stride FS
+        // ---- plane scatter + d_xyz ----------------------------------------------------------
+        for (int g = warp; g < DT; g += DTHREADS / 32) {
+            const int gi = g0 + g;
+            if (gi >= a.P) continue;
+            float ph[4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
+            ph[3] = a.time;
+            float dph[3] = {0.f, 0.f, 0.f};    // this lane's share of dL/dp_hat
+            for (int l = 0; l < L; ++l) {
+                Tap tp[6];
+                float v[6][4], s[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int ca = kCombA[k], cb = kCombB[k];
+                    tp[k] = make_tap(ph[ca], ph[cb], n.reso[l][ca], n.reso[l][cb]);
+                    const float* pl = n.planes[l][k];
+                    v[k][0] = tap_fetch(pl, tp[k].o00, lane); v[k][1] = tap_fetch(pl, tp[k].o01, lane);
+                    v[k][2] = tap_fetch(pl, tp[k].o10, lane); v[k][3] = tap_fetch(pl, tp[k].o11, lane);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    s[k] = tp[k].w00 * v[k][0] + tp[k].w01 * v[k][1] + tp[k].w10 * v[k][2] + tp[k].w11 * v[k][3];
+                const float df = sm.A[g * FS + l * FD + lane];
+                // prefix / suffix products: ds_k = df * prod_{j != k} s_j
+                float pre[6], suf[6];
+                pre[0] = 1.f;
+#pragma unroll
+                for (int k = 1; k < 6; ++k) pre[k] = pre[k - 1] * s[k - 1];
+                suf[5] = 1.f;
+#pragma unroll
+                for (int k = 4; k >= 0; --k) suf[k] = suf[k + 1] * s[k + 1];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float ds = df * pre[k] * suf[k];
+                    float* gp = a.gplanes[l][k];
+                    if (tp[k].o00 >= 0) atomicAdd(gp + (size_t)tp[k].o00 * FD + lane, tp[k].w00 * ds);
+                    if (tp[k].o01 >= 0) atomicAdd(gp + (size_t)tp[k].o01 * FD + lane, tp[k].w01 * ds);
+                    if (tp[k].o10 >= 0) atomicAdd(gp + (size_t)tp[k].o10 * FD + lane, tp[k].w10 * ds);
+                    if (tp[k].o11 >= 0) atomicAdd(gp + (size_t)tp[k].o11 * FD + lane, tp[k].w11 * ds);
+                    // d(sample)/d(ix), d(sample)/d(iy)
+                    const float dsx = (v[k][1] - v[k][0]) * (1.f - tp[k].fy) + (v[k][3] - v[k][2]) * tp[k].fy;
+                    const float dsy = (v[k][2] - v[k][0]) * (1.f - tp[k].fx) + (v[k][3] - v[k][1]) * tp[k].fx;
+                    const int ca = kCombA[k], cb = kCombB[k];
+                    if (ca < 3) dph[ca] += ds * dsx * tp[k].gx;
+                    if (cb < 3) dph[cb] += ds * dsy * tp[k].gy;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dph[c] += __shfl_xor_sync(0xffffffffu, dph[c], o);
+            }
+            if (lane < 3) {
+                const float gridp = dph[lane] * n.inv_span2[lane];
+                a.d_xyz[(size_t)gi * 3 + lane] = ldz(a.g_means, (size_t)gi * 3 + lane) + gridp + sm.G[g * 16 + 11 + lane];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// sum the per-CTA partial Linear gradients: one block per segment
+struct ReduceSeg { float* dst; int off; int count; };
+struct ReduceArgs { ReduceSeg seg[32]; int nseg; const float* partial; int stride; int nparts; };
+__global__ void __launch_bounds__(256) deform_reduce_kernel(ReduceArgs r) {
+    const ReduceSeg sg = r.seg[blockIdx.x];
+    for (int i = threadIdx.x; i < sg.count; i += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < r.nparts; ++p) s += r.partial[(size_t)p * r.stride + sg.off + i];
+        sg.dst[i] = s;
+    }
+}
+
+}  // namespace s3g

@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1280)
     ap.add_argument("--mode", default="sh", choices=["sh", "rgb"])
+    ap.add_argument("--workload", default="raster", choices=["raster", "fine"],
+                    help="raster: rasterizer fwd+bwd (BASELINE metric, default). fine: full render() of the fine stage - "
+                         "HexPlane + decoder + rgb/depth pass + feat pass, fwd+bwd (BASELINE config 3 shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=500_000)
@@ -130,6 +133,8 @@ def main():
     import util
 
     P, W, H = a.points, a.width, a.height
+    if a.workload == "fine":
+        return main_fine(a, rank, world, local, dev)
     cloud = syn.make_cloud(P, seed=0)
     ring = syn.waymo_ring(W, H, frames=50)
     cam = ring[1 + 3 * ((rank * 6) % 50)]          # front camera of frame 6*rank
@@ -313,6 +318,152 @@ def main():
         out["stages"] = stages
         if cpu:
             out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_fine(a, rank, world, local, dev):
+    """BASELINE config 3 shape at --points Gaussians: render(stage='fine', return_dx, render_feat) + the training
+    loss terms that touch the path (train.py:395-425 without SSIM / plane regularisers) + backward."""
+    from s3gaussian_b200 import synthetic as syn
+    import util
+    P, W, H = a.points, a.width, a.height
+    cloud = syn.make_cloud(P, seed=0)
+    ring = syn.waymo_ring(W, H, frames=50)
+    cam = ring[1 + 3 * ((rank * 6) % 50)].to(dev)
+    cam.time = 0.37 if rank == 0 else cam.time
+    state = syn.make_deform_state(0, weight_scale=0.2)
+    bg = torch.zeros(3, device=dev)
+    gt_img = torch.rand(3, H, W).pin_memory()
+    gt_dep = (torch.rand(1, H, W) * 50).pin_memory()
+    gt_feat = torch.rand(3, H, W).pin_memory()
+    h2d_bytes = (gt_img.numel() + gt_dep.numel() + gt_feat.numel()) * 4
+    if a.impl == "ours":
+        from s3gaussian_b200 import build, _lib
+        build.build()
+        from s3gaussian_b200.deformation import deform_network
+        from s3gaussian_b200.gaussian_renderer import render, PipelineParams, GaussianModelLite
+        import ref_ext
+        net = deform_network(ref_ext.ref_deform_args(syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES))
+        net.deformation_net.set_aabb(*[list(x) for x in syn.WAYMO_AABB])
+        net.load_state_dict(state, strict=False)
+        pc = GaussianModelLite(cloud, net).to(dev)
+        leaves = [p for p in pc.parameters()]
+        pipe = PipelineParams()
+        do_render = lambda: render(cam, pc, pipe, bg, stage="fine", return_dx=True, render_feat=True)
+    else:
+        import ref_ext
+        if not (ref_ext.available() and ref_ext.deform_available()):
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return
+        stack = util.RefFineStack(cloud, state, dev, syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES)
+        leaves = stack.leaves()
+        do_render = lambda: stack.render(cam, bg, render_feat=True)
+    img_d, dep_d, feat_d = gt_img.to(dev), gt_dep.to(dev), gt_feat.to(dev)
+
+    def loss_of(out, im, de, fe):
+        return ((out["render"] - im).abs().mean() + 0.5 * ((out["depth"] - de) ** 2).mean() +
+                0.001 * ((out["feat"] - fe) ** 2).mean() + 0.001 * out["dx"].abs().mean() + 0.001 * out["dshs"].abs().mean())
+
+    def sync_grads():
+        if world > 1:
+            flat = torch.cat([v.grad.reshape(-1) for v in leaves if v.grad is not None])
+            dist.all_reduce(flat)
+
+    def step_resident():
+        for v in leaves:
+            v.grad = None
+        loss_of(do_render(), img_d, dep_d, feat_d).backward()
+        sync_grads()
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e():
+        for v in leaves:
+            v.grad = None
+        im, de, fe = gt_img.to(dev, non_blocking=True), gt_dep.to(dev, non_blocking=True), gt_feat.to(dev, non_blocking=True)
+        loss = loss_of(do_render(), im, de, fe)
+        loss.backward()
+        sync_grads()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        return ms
+
+    sampler = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
+    if sampler:
+        sampler.start()
+    ms_res = timed(step_resident, a.steps, max(a.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, a.steps, 3)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.impl == "ours":
+        # north_star: the reference's PyTorch HexPlane/deformation path on the box's host cores
+        import ref_ext
+        n = 100_000
+        if ref_ext.deform_available():
+            dn, _ = ref_ext.load_ref_deform()
+            cnet = dn(ref_ext.ref_deform_args(syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES))
+            cnet.deformation_net.set_aabb(*[list(x) for x in syn.WAYMO_AABB])
+            cnet.load_state_dict(state, strict=False)
+            torch.set_num_threads(os.cpu_count())
+            x = cloud.xyz[:n].clone().requires_grad_(True)
+            sh = cloud.get_features()[:n].clone().requires_grad_(True)
+            t = torch.full((n, 1), 0.37)
+
+            def cpu_step():
+                for p_ in cnet.parameters():
+                    p_.grad = None
+                o = cnet(x, cloud.scaling[:n], cloud.rotation[:n], cloud.opacity[:n], sh, t)
+                (o[0].sum() + o[5].abs().mean() + o[6].sum() + o[7].abs().mean()).backward()
+            cpu_step()
+            t0 = time.time()
+            reps = 3
+            for _ in range(reps):
+                cpu_step()
+            dt = (time.time() - t0) / reps
+            cpu = {"value": round(n / dt, 1), "unit": "Gaussians/s", "cores": torch.get_num_threads(), "kind": "reference",
+                   "sample": f"reference scene/deformation.py deform_network fwd+bwd on {n} of the workload's Gaussians, "
+                             f"PyTorch CPU, {torch.get_num_threads()} threads of {os.cpu_count()} cores, {dt:.2f} s per pass "
+                             "(HexPlane + decoder only: the rasterizer has no CPU implementation upstream)"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    step_ms, e2e_ms = ms_res / a.steps, ms_e2e / a.steps
+    out = {"metric": "fwd+bwd Gaussians/s (full fine-stage render(): HexPlane + decoder + rgb/depth pass + feat pass)",
+           "value": round(world * P / (step_ms * 1e-3), 1), "unit": "Gaussians/s", "n_gpus": world, "steps": a.steps,
+           "warmup": max(a.warmup, 3), "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"fine-stage render() of {P} Gaussians at {W}x{H}: default HexPlane (4 levels x 6 planes x 32 ch, "
+                                  "35.8M params) + dx/dshs/feat heads, two rasterizer passes, L1+depth+feat+dx+dshs loss, backward",
+                      "points": P, "width": W, "height": H, "parallelism": f"view-parallel dp{world}"},
+           "e2e": {"value": round(world * P / (e2e_ms * 1e-3), 1), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4),
+                   "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+           "gpu_launches": ((16 + 16 + 2 + 4) * a.steps) if a.impl == "ours" else 0, "clocks": clocks}
+    if a.impl == "reference":
+        out["impl"] = "reference"
+    elif cpu:
+        out["cpu_baseline"] = cpu
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

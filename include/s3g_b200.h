@@ -203,20 +203,23 @@ typedef struct s3g_deform_net_grads {
  * rot_act [P,4] = normalize(rot+dr), opacity_act [P,1] = sigmoid(opacity+do),
  * colors [P,3] = clamp_min(SH(shs+dshs, dir(xyz - campos)) + 0.5, 0) with the UNDEFORMED xyz,
  * dx [P,3], dshs [P,16,3], feat [P,3].  Pointers of disabled heads may be NULL.
+ * features [P, 32*num_levels] receives the sampled HexPlane features (the hand-over between the
+ * sampling and the decoder kernel); keep it for s3g_deform_backward.
  * campos: device float[3]; sh_degree: active degree (0..3). */
 int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
                        const float* rotations, const float* opacity, const float* shs, float time,
                        const float* campos, int sh_degree,
                        float* means3D, float* scales_act, float* rot_act, float* opacity_act,
-                       float* colors, float* dx, float* dshs, float* feat, void* stream);
+                       float* colors, float* dx, float* dshs, float* feat, float* features, void* stream);
 
 /* Backward of the above.  g_* are dL/d(output) (NULL = zero).  Writes dL/d(raw inputs)
  * [P,*] in full, overwrites the Linear gradients in `grads` and accumulates the plane
- * gradients.  `workspace` must hold s3g_deform_workspace_bytes() bytes. */
-size_t s3g_deform_workspace_bytes(const s3g_deform_net* net);
+ * gradients.  `features` is the buffer the forward filled.  `workspace` must hold
+ * s3g_deform_workspace_bytes(net, P) bytes. */
+size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P);
 int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
                         const float* rotations, const float* opacity, const float* shs, float time,
-                        const float* campos, int sh_degree,
+                        const float* campos, int sh_degree, const float* features,
                         const float* g_means3D, const float* g_scales_act, const float* g_rot_act,
                         const float* g_opacity_act, const float* g_colors, const float* g_dx,
                         const float* g_dshs, const float* g_feat,

@@ -6,6 +6,8 @@
 // C ABI.  No torch, no CPU fallback: every path ends in a kernel launch on the
 // caller's stream or in an error code.
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -492,7 +494,7 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
                        const float* rotations, const float* opacity, const float* shs, float time,
                        const float* campos, int sh_degree, float* means3D, float* scales_act,
                        float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
-                       float* feat, void* stream_) {
+                       float* feat, float* features, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
     if (P == 0) return S3G_OK;
@@ -501,13 +503,24 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
     if (rc != S3G_OK) return rc;
     if (!xyz || !scales || !rotations || !opacity || !shs || !campos)
         return fail(S3G_ERR_ARG, "deform_forward: null input");
-    if (!means3D || !scales_act || !rot_act || !opacity_act || !colors)
+    if (!means3D || !scales_act || !rot_act || !opacity_act || !colors || !features)
         return fail(S3G_ERR_ARG, "deform_forward: null output");
     if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_forward: sh_degree must be 0..3");
     a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
     a.campos = campos; a.time = time; a.sh_degree = sh_degree;
     a.o_means = means3D; a.o_scales = scales_act; a.o_rot = rot_act; a.o_opacity = opacity_act;
-    a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat;
+    a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat; a.features = features;
+    {
+        SampleArgs sa;
+        sa.net = a.net; sa.P = P; sa.xyz = xyz; sa.time = time; sa.features = features;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int blocks = std::min((P + 7) / 8, sms * 12);
+        if (a.net.L == 4) hexplane_sample_kernel<4><<<blocks, 256, 0, stream>>>(sa);
+        else hexplane_sample_kernel<0><<<blocks, 256, 0, stream>>>(sa);
+        S3G_CUDA(cudaGetLastError(), "hexplane_sample launch");
+    }
     const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
     const int ntiles = (P + DT - 1) / DT;
     if (a.net.L == 4) {
@@ -547,18 +560,19 @@ int bwd_grid(int ntiles) {
 constexpr int kMaxBwdGrid = 256;
 }  // namespace
 
-size_t s3g_deform_workspace_bytes(const s3g_deform_net* net) {
+size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
     DNet d;
     if (to_dnet(net, d) != S3G_OK) return 0;
     GradOff o;
     make_offsets(d, o);
-    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 256;
+    // per-CTA partial Linear gradients + dL/d(features) [P][32L]
+    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float);
 }
 
 int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
                         const float* rotations, const float* opacity, const float* shs, float time,
-                        const float* campos, int sh_degree, const float* g_means3D,
-                        const float* g_scales_act, const float* g_rot_act, const float* g_opacity_act,
+                        const float* campos, int sh_degree, const float* features,
+                        const float* g_means3D, const float* g_scales_act, const float* g_rot_act, const float* g_opacity_act,
                         const float* g_colors, const float* g_dx, const float* g_dshs, const float* g_feat,
                         float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
                         const s3g_deform_net_grads* grads, void* workspace, void* stream_) {
@@ -568,7 +582,7 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
     int rc = to_dnet(net, a.net);
     if (rc != S3G_OK) return rc;
     if (!grads || !workspace) return fail(S3G_ERR_ARG, "deform_backward: null grads/workspace");
-    if (P > 0 && (!xyz || !scales || !rotations || !opacity || !shs || !campos))
+    if (P > 0 && (!xyz || !scales || !rotations || !opacity || !shs || !campos || !features))
         return fail(S3G_ERR_ARG, "deform_backward: null input");
     if (P > 0 && (!d_xyz || !d_scales || !d_rotations || !d_opacity || !d_shs))
         return fail(S3G_ERR_ARG, "deform_backward: null output");
@@ -586,6 +600,8 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
         }
     make_offsets(d, a.off);
     a.partial = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    a.features = features;
+    a.dfeatures = a.partial + (size_t)kMaxBwdGrid * a.off.total;
     const int ntiles = (P + DT - 1) / DT;
     int grid = bwd_grid(ntiles);
     if (grid > kMaxBwdGrid) grid = kMaxBwdGrid;
@@ -622,8 +638,22 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
             deform_backward_kernel<0><<<grid, DTHREADS, smem, stream>>>(a);
         }
         S3G_CUDA(cudaGetLastError(), "deform_backward launch");
+        ScatterArgs sc;
+        sc.net = a.net; sc.P = P; sc.xyz = xyz; sc.time = time; sc.dfeatures = a.dfeatures; sc.d_xyz = d_xyz;
+        for (int l = 0; l < S3G_MAX_LEVELS; ++l)
+            for (int k = 0; k < 6; ++k) sc.gplanes[l][k] = l < d.L ? a.gplanes[l][k] : nullptr;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int blocks = std::min((P + 7) / 8, sms * 8);
+        hexplane_scatter_kernel<<<blocks, 256, 0, stream>>>(sc);
+        S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
     }
-    deform_reduce_kernel<<<r.nseg, 256, 0, stream>>>(r);
+    {
+        int maxc = 1;
+        for (int i = 0; i < r.nseg; ++i) maxc = std::max(maxc, r.seg[i].count);
+        deform_reduce_kernel<<<dim3((maxc + 255) / 256, r.nseg), 256, 0, stream>>>(r);
+    }
     S3G_CUDA(cudaGetLastError(), "deform_reduce launch");
     return S3G_OK;
 }

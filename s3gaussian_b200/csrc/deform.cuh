@@ -44,8 +44,10 @@ struct DNet {                     // device-side view of s3g_deform_net
     const float *w_d0, *b_d0, *w_d2, *b_d2, *w_d4, *b_d4;
 };
 
-__constant__ int kCombA[6] = {0, 0, 0, 1, 1, 2};
-__constant__ int kCombB[6] = {1, 2, 3, 2, 3, 3};
+// plane k samples coordinates (a,b): (0,1),(0,2),(0,3),(1,2),(1,3),(2,3) - compile-time so that
+// unrolled loops index register arrays statically
+__host__ __device__ constexpr int comb_a(int k) { return k < 3 ? 0 : (k < 5 ? 1 : 2); }
+__host__ __device__ constexpr int comb_b(int k) { return k == 0 ? 1 : (k == 1 ? 2 : (k == 2 ? 3 : (k == 3 ? 2 : 3))); }
 
 // ---- 3xTF32 tensor-core tile product ----------------------------------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -145,91 +147,70 @@ __device__ __forceinline__ void tile_small_out(const float* sIn, int inStride, c
 }
 
 // ---- HexPlane sampling -------------------------------------------------------
-struct Tap {       // one bilinear footprint (torch grid_sample, align_corners=True, border padding)
-    int o00, o01, o10, o11;      // texel offsets (in texels), -1 = out of range (weight contributes 0)
-    float w00, w01, w10, w11;
-    float gx, gy;                // d(ix)/d(p_hat) chain factors incl. the border-clamp mask
-    float fx, fy;                // fractional parts
+// torch grid_sample(bilinear, align_corners=True, padding_mode='border') separates per axis:
+// ix = clamp((x+1)/2*(R-1), 0, R-1), i0 = floor(ix), f = ix - i0, neighbours i0 and i0+1 with
+// weights (1-f) and f.  When i0+1 falls outside, f is exactly 0, so the neighbour index is
+// clamped instead of predicated (its weight is 0).  One AxisTap per (level, axis) is shared by
+// the three planes that use the axis - the per-plane work is 2 IMADs, 4 loads, 8 multiplies.
+struct AxisTap {
+    int i0, i1;          // texel indices (i1 clamped to R-1)
+    float f, omf;        // fractional part and 1 - f
+    float g;             // d(ix)/d(p_hat): (R-1)/2 inside, 0 where border-clamped
 };
-__device__ __forceinline__ Tap make_tap(float x, float y, int W, int H) {
-    Tap t;
-    float ix = ((x + 1.f) * 0.5f) * (float)(W - 1);
-    float iy = ((y + 1.f) * 0.5f) * (float)(H - 1);
-    // clip_coordinates: gradient is zero outside [0, size-1]
-    t.gx = (ix <= 0.f || ix >= (float)(W - 1)) ? 0.f : 0.5f * (float)(W - 1);
-    t.gy = (iy <= 0.f || iy >= (float)(H - 1)) ? 0.f : 0.5f * (float)(H - 1);
-    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
-    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
-    const float x0f = floorf(ix), y0f = floorf(iy);
-    const int x0 = (int)x0f, y0 = (int)y0f;
-    const float fx = ix - x0f, fy = iy - y0f;
-    t.fx = fx; t.fy = fy;
-    t.w00 = (1.f - fx) * (1.f - fy);
-    t.w01 = fx * (1.f - fy);
-    t.w10 = (1.f - fx) * fy;
-    t.w11 = fx * fy;
-    const bool xin = x0 + 1 <= W - 1, yin = y0 + 1 <= H - 1;
-    t.o00 = y0 * W + x0;
-    t.o01 = xin ? y0 * W + x0 + 1 : -1;
-    t.o10 = yin ? (y0 + 1) * W + x0 : -1;
-    t.o11 = (xin && yin) ? (y0 + 1) * W + x0 + 1 : -1;
+__device__ __forceinline__ AxisTap axis_tap(float x, int R) {
+    AxisTap t;
+    const float m = (float)(R - 1);
+    float ix = ((x + 1.f) * 0.5f) * m;
+    t.g = (ix <= 0.f || ix >= m) ? 0.f : 0.5f * m;     // clip_coordinates_set_grad
+    ix = fminf(fmaxf(ix, 0.f), m);
+    const float i0f = floorf(ix);
+    t.i0 = (int)i0f;
+    t.i1 = min(t.i0 + 1, R - 1);
+    t.f = ix - i0f;
+    t.omf = 1.f - t.f;
     return t;
 }
-__device__ __forceinline__ float tap_fetch(const float* __restrict__ plane, int off, int lane) {
-    return off >= 0 ? __ldg(plane + (size_t)off * FD + lane) : 0.f;
-}
 
-// features of one Gaussian (this lane's channel) for all levels -> sFrow[32*l + lane].
-// With a compile-time level count every tap address is computed first and all
-// 24*L 128-byte loads are in flight together (the phase is latency-bound otherwise).
+// features of one Gaussian (this lane's channel) for all levels -> sFrow[32*l + lane]; two levels
+// (48 independent 128-byte loads) are in flight at a time.
 template <int LT>
 __device__ __forceinline__ void sample_gaussian(const DNet& n, const float ph[4], int lane, float* sFrow) {
-    if constexpr (LT > 0 && (LT % 2) == 0) {
-        // two levels (48 loads) in flight at a time: 96 live texel registers spill
-#pragma unroll 1
-        for (int l0 = 0; l0 < LT; l0 += 2) {
-            float v[2][6][4];
-            float fx[2][6], fy[2][6];
+    const int L = LT > 0 ? LT : n.L;
+    for (int l0 = 0; l0 < L; l0 += 2) {
+        float v[2][6][4];
+        AxisTap ax[2][4];
 #pragma unroll
-            for (int dl = 0; dl < 2; ++dl) {
+        for (int dl = 0; dl < 2; ++dl) {
+            const int l = min(l0 + dl, L - 1);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int a = kCombA[k], b = kCombB[k];
-                    const Tap t = make_tap(ph[a], ph[b], n.reso[l0 + dl][a], n.reso[l0 + dl][b]);
-                    const float* pl = n.planes[l0 + dl][k];
-                    v[dl][k][0] = tap_fetch(pl, t.o00, lane);
-                    v[dl][k][1] = tap_fetch(pl, t.o01, lane);
-                    v[dl][k][2] = tap_fetch(pl, t.o10, lane);
-                    v[dl][k][3] = tap_fetch(pl, t.o11, lane);
-                    fx[dl][k] = t.fx; fy[dl][k] = t.fy;
-                }
+            for (int d = 0; d < 4; ++d) ax[dl][d] = axis_tap(ph[d], n.reso[l][d]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int a = comb_a(k), b = comb_b(k);
+                const int W = n.reso[l][a];
+                const float* pl = n.planes[l][k] + lane;
+                const int r0 = ax[dl][b].i0 * W, r1 = ax[dl][b].i1 * W;
+                v[dl][k][0] = __ldg(pl + (size_t)(r0 + ax[dl][a].i0) * FD);
+                v[dl][k][1] = __ldg(pl + (size_t)(r0 + ax[dl][a].i1) * FD);
+                v[dl][k][2] = __ldg(pl + (size_t)(r1 + ax[dl][a].i0) * FD);
+                v[dl][k][3] = __ldg(pl + (size_t)(r1 + ax[dl][a].i1) * FD);
             }
+        }
 #pragma unroll
-            for (int dl = 0; dl < 2; ++dl) {
+        for (int dl = 0; dl < 2; ++dl) {
+            if (l0 + dl < L) {
                 float f = 1.f;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
-                    const float x = fx[dl][k], y = fy[dl][k];
-                    const float s = (1.f - x) * (1.f - y) * v[dl][k][0] + x * (1.f - y) * v[dl][k][1] +
-                                    (1.f - x) * y * v[dl][k][2] + x * y * v[dl][k][3];
+                    const AxisTap& X = ax[dl][comb_a(k)];
+                    const AxisTap& Y = ax[dl][comb_b(k)];
+                    const float s = (X.omf * Y.omf) * v[dl][k][0] + (X.f * Y.omf) * v[dl][k][1] +
+                                    (X.omf * Y.f) * v[dl][k][2] + (X.f * Y.f) * v[dl][k][3];
                     f = (k == 0) ? s : f * s;     // interp_space = 1 * s0 * s1 * ... (hexplane.py:87-96)
                 }
                 sFrow[(l0 + dl) * FD + lane] = f;
             }
         }
-        return;
-    }
-    for (int l = 0; l < n.L; ++l) {
-        float v[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int a = kCombA[k], b = kCombB[k];
-            const Tap t = make_tap(ph[a], ph[b], n.reso[l][a], n.reso[l][b]);
-            const float* pl = n.planes[l][k];
-            v[k] = t.w00 * tap_fetch(pl, t.o00, lane) + t.w01 * tap_fetch(pl, t.o01, lane) +
-                   t.w10 * tap_fetch(pl, t.o10, lane) + t.w11 * tap_fetch(pl, t.o11, lane);
-        }
-        sFrow[l * FD + lane] = ((((v[0] * v[1]) * v[2]) * v[3]) * v[4]) * v[5];
     }
 }
 
@@ -262,7 +243,52 @@ struct DeformFwdArgs {
     float time;
     int sh_degree;
     float *o_means, *o_scales, *o_rot, *o_opacity, *o_colors, *o_dx, *o_dshs, *o_feat;
+    float* features;     // [P][32L] written by hexplane_sample_kernel, read by the decoder tiles
 };
+
+// ---- stage 1: HexPlane sampling, one warp per Gaussian, high occupancy ---------------
+// The gather (12 KB of texels per Gaussian, L2-resident planes) is latency-bound unless many
+// warps keep loads in flight, which the shared-memory-heavy decoder CTAs cannot; it is its own
+// kernel and hands the [P][32L] features over through HBM (1 GB at 2M Gaussians, ~0.3 ms).
+struct SampleArgs {
+    DNet net;
+    int P;
+    const float* xyz;
+    float time;
+    float* features;
+};
+template <int LT>
+__global__ void __launch_bounds__(256, 3) hexplane_sample_kernel(SampleArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int FL = FD * a.net.L;
+    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.P; g += gridDim.x * wpb) {
+        float ph[4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)g * 3 + c) - a.net.aabb0[c]) * a.net.inv_span2[c] - 1.0f;
+        ph[3] = a.time;
+        sample_gaussian<LT>(a.net, ph, lane, a.features + (size_t)g * FL);
+    }
+}
+
+// load / store a [64][32L] tile of per-Gaussian rows between global memory and smem rows of stride FS
+__device__ __forceinline__ void tile_rows_load(const float* __restrict__ gsrc, int g0, int P, int FL, float* sDst, int FS) {
+    const int n4 = FL / 4;
+    for (int i = threadIdx.x; i < DT * n4; i += DTHREADS) {
+        const int g = i / n4, c4 = i - g * n4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g0 + g < P) v = __ldg(reinterpret_cast<const float4*>(gsrc + (size_t)(g0 + g) * FL) + c4);
+        *reinterpret_cast<float4*>(sDst + g * FS + 4 * c4) = v;
+    }
+}
+__device__ __forceinline__ void tile_rows_store(float* __restrict__ gdst, int g0, int P, int FL, const float* sSrc, int FS) {
+    const int n4 = FL / 4;
+    for (int i = threadIdx.x; i < DT * n4; i += DTHREADS) {
+        const int g = i / n4, c4 = i - g * n4;
+        if (g0 + g < P)
+            *(reinterpret_cast<float4*>(gdst + (size_t)(g0 + g) * FL) + c4) = *reinterpret_cast<const float4*>(sSrc + g * FS + 4 * c4);
+    }
+}
 
 // smem carve (floats).  FS = 32L+4.
 struct DeformSmem {
@@ -304,14 +330,8 @@ __global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdAr
             sm.X[g * 4 + c] = (g0 + g < a.P) ? a.xyz[(size_t)(g0 + g) * 3 + c] : 0.f;
         }
         __syncthreads();
-        // ---- 1. HexPlane sampling: warp w takes Gaussians w, w+8, ... --------
-        for (int g = warp; g < DT; g += DTHREADS / 32) {
-            float ph[4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
-            ph[3] = a.time;
-            sample_gaussian<LT>(n, ph, lane, sm.F + g * FS);
-        }
+        // ---- 1. features of the tile (sampled by hexplane_sample_kernel) ---------
+        tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
         __syncthreads();
         // ---- 2. decoder ------------------------------------------------------
         // h = feature_out(f)
@@ -489,16 +509,17 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
             split_tf32(b[1], bh[1], bl[1]);
             mma3(acc, ah, al, bh, bl);
         }
-        float2* p0 = reinterpret_cast<float2*>(gW + (size_t)(m0 + g) * NIN + n0 + 2 * t);
-        float2* p1 = reinterpret_cast<float2*>(gW + (size_t)(m0 + g + 8) * NIN + n0 + 2 * t);
-        float2 v0 = *p0, v1 = *p1;
-        v0.x += acc[0]; v0.y += acc[1]; v1.x += acc[2]; v1.y += acc[3];
-        *p0 = v0; *p1 = v1;
+        // fire-and-forget REDs on the CTA-private partial buffer: a load-add-store would expose
+        // one L2 round trip per output tile (measured: 14 ms of a 55 ms step)
+        float* p0 = gW + (size_t)(m0 + g) * NIN + n0 + 2 * t;
+        float* p1 = gW + (size_t)(m0 + g + 8) * NIN + n0 + 2 * t;
+        atomicAdd(p0, acc[0]); atomicAdd(p0 + 1, acc[1]);
+        atomicAdd(p1, acc[2]); atomicAdd(p1 + 1, acc[3]);
     }
     if (threadIdx.x < M) {
         float sacc = 0.f;
         for (int k = 0; k < DT; ++k) sacc += sDelta[k * dStride + threadIdx.x];
-        gb[threadIdx.x] += sacc;
+        atomicAdd(gb + threadIdx.x, sacc);
     }
 }
 
@@ -514,12 +535,12 @@ __device__ __forceinline__ void small_head_backward(const float* sDout, int k, c
         if (o < k) {
             float sacc = 0.f;
             for (int g = 0; g < DT; ++g) sacc = fmaf(sDout[g * 4 + o], sAct[g * aStride + j], sacc);
-            gW2[o * HWID + j] += sacc;
+            atomicAdd(gW2 + o * HWID + j, sacc);
         }
         if (tid < k) {
             float sb = 0.f;
             for (int g = 0; g < DT; ++g) sb += sDout[g * 4 + tid];
-            gb2[tid] += sb;
+            atomicAdd(gb2 + tid, sb);
         }
     }
     for (int e = tid; e < DT * HWID; e += DTHREADS) {
@@ -548,6 +569,8 @@ struct DeformBwdArgs {
     float *d_xyz, *d_scales, *d_rot, *d_opacity, *d_shs;
     float* gplanes[S3G_MAX_LEVELS][6];
     float* partial;      // [gridDim.x][off.total]
+    const float* features;   // [P][32L] from the forward
+    float* dfeatures;        // [P][32L] dL/d(features), consumed by hexplane_scatter_kernel
     GradOff off;
 };
 
@@ -607,14 +630,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
         }
         for (int i = tid; i < DT * HS; i += DTHREADS) sm.DH[i] = 0.f;
         __syncthreads();
-        // ---- recompute: features and hidden -----------------------------------
-        for (int g = warp; g < DT; g += DTHREADS / 32) {
-            float ph[4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
-            ph[3] = a.time;
-            sample_gaussian<LT>(n, ph, lane, sm.F + g * FS);
-        }
+        // ---- features of the tile (saved by the forward), hidden recomputed -------
+        tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
         __syncthreads();
         if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
         else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
@@ -868,79 +885,119 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
         else if (L == 2) feat_layers_bwd<64>(sm, n, part, a.off, FS);
         else if (L == 3) feat_layers_bwd<96>(sm, n, part, a.off, FS);
         else if (L == 8) feat_layers_bwd<256>(sm, n, part, a.off, FS);
-        // DF now lives in sm.A with row stride FS
-        // ---- plane scatter + d_xyz ----------------------------------------------------------
-        for (int g = warp; g < DT; g += DTHREADS / 32) {
-            const int gi = g0 + g;
-            if (gi >= a.P) continue;
-            float ph[4];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) ph[c] = (sm.X[g * 4 + c] - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
-            ph[3] = a.time;
-            float dph[3] = {0.f, 0.f, 0.f};    // this lane's share of dL/dp_hat
-            for (int l = 0; l < L; ++l) {
-                Tap tp[6];
-                float v[6][4], s[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int ca = kCombA[k], cb = kCombB[k];
-                    tp[k] = make_tap(ph[ca], ph[cb], n.reso[l][ca], n.reso[l][cb]);
-                    const float* pl = n.planes[l][k];
-                    v[k][0] = tap_fetch(pl, tp[k].o00, lane); v[k][1] = tap_fetch(pl, tp[k].o01, lane);
-                    v[k][2] = tap_fetch(pl, tp[k].o10, lane); v[k][3] = tap_fetch(pl, tp[k].o11, lane);
-                }
-#pragma unroll
-                for (int k = 0; k < 6; ++k)
-                    s[k] = tp[k].w00 * v[k][0] + tp[k].w01 * v[k][1] + tp[k].w10 * v[k][2] + tp[k].w11 * v[k][3];
-                const float df = sm.A[g * FS + l * FD + lane];
-                // prefix / suffix products: ds_k = df * prod_{j != k} s_j
-                float pre[6], suf[6];
-                pre[0] = 1.f;
-#pragma unroll
-                for (int k = 1; k < 6; ++k) pre[k] = pre[k - 1] * s[k - 1];
-                suf[5] = 1.f;
-#pragma unroll
-                for (int k = 4; k >= 0; --k) suf[k] = suf[k + 1] * s[k + 1];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const float ds = df * pre[k] * suf[k];
-                    float* gp = a.gplanes[l][k];
-                    if (tp[k].o00 >= 0) atomicAdd(gp + (size_t)tp[k].o00 * FD + lane, tp[k].w00 * ds);
-                    if (tp[k].o01 >= 0) atomicAdd(gp + (size_t)tp[k].o01 * FD + lane, tp[k].w01 * ds);
-                    if (tp[k].o10 >= 0) atomicAdd(gp + (size_t)tp[k].o10 * FD + lane, tp[k].w10 * ds);
-                    if (tp[k].o11 >= 0) atomicAdd(gp + (size_t)tp[k].o11 * FD + lane, tp[k].w11 * ds);
-                    // d(sample)/d(ix), d(sample)/d(iy)
-                    const float dsx = (v[k][1] - v[k][0]) * (1.f - tp[k].fy) + (v[k][3] - v[k][2]) * tp[k].fy;
-                    const float dsy = (v[k][2] - v[k][0]) * (1.f - tp[k].fx) + (v[k][3] - v[k][1]) * tp[k].fx;
-                    const int ca = kCombA[k], cb = kCombB[k];
-                    if (ca < 3) dph[ca] += ds * dsx * tp[k].gx;
-                    if (cb < 3) dph[cb] += ds * dsy * tp[k].gy;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dph[c] += __shfl_xor_sync(0xffffffffu, dph[c], o);
-            }
-            if (lane < 3) {
-                const float gridp = dph[lane] * n.inv_span2[lane];
-                a.d_xyz[(size_t)gi * 3 + lane] = ldz(a.g_means, (size_t)gi * 3 + lane) + gridp + sm.G[g * 16 + 11 + lane];
-            }
+        // DF now lives in sm.A with row stride FS: hand it to the scatter kernel, and write the
+        // part of d_xyz that does not go through the planes (identity path + SH view direction)
+        tile_rows_store(a.dfeatures, g0, a.P, FD * L, sm.A, FS);
+        if (tid < DT * 3) {
+            const int g = tid / 3, c = tid - 3 * g, gi = g0 + g;
+            if (gi < a.P) a.d_xyz[(size_t)gi * 3 + c] = ldz(a.g_means, (size_t)gi * 3 + c) + sm.G[g * 16 + 11 + c];
         }
         __syncthreads();
     }
 }
 
-// sum the per-CTA partial Linear gradients: one block per segment
+// ---- plane-gradient scatter + d(xyz) through the bilinear weights --------------------
+// One warp per Gaussian, lane = channel: every tap is one 128-byte-wide RED.
+struct ScatterArgs {
+    DNet net;
+    int P;
+    const float* xyz;
+    float time;
+    const float* dfeatures;               // [P][32L]
+    float* gplanes[S3G_MAX_LEVELS][6];
+    float* d_xyz;                          // [P,3], += grid path
+};
+__global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a) {
+    const DNet& n = a.net;
+    const int L = n.L;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int FL = FD * L;
+    for (int gi = blockIdx.x * wpb + (threadIdx.x >> 5); gi < a.P; gi += gridDim.x * wpb) {
+        float ph[4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gi * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
+        ph[3] = a.time;
+        float dph[3] = {0.f, 0.f, 0.f};    // this lane's share of dL/dp_hat
+        for (int l = 0; l < L; ++l) {
+            AxisTap ax[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) ax[d] = axis_tap(ph[d], n.reso[l][d]);
+            float v[6][4], s[6];
+            int o00[6], o01[6], o10[6], o11[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int ca = comb_a(k), cb = comb_b(k);
+                const int W = n.reso[l][ca];
+                const float* pl = n.planes[l][k] + lane;
+                const int r0 = ax[cb].i0 * W, r1 = ax[cb].i1 * W;
+                o00[k] = (r0 + ax[ca].i0) * FD; o01[k] = (r0 + ax[ca].i1) * FD;
+                o10[k] = (r1 + ax[ca].i0) * FD; o11[k] = (r1 + ax[ca].i1) * FD;
+                v[k][0] = __ldg(pl + o00[k]); v[k][1] = __ldg(pl + o01[k]);
+                v[k][2] = __ldg(pl + o10[k]); v[k][3] = __ldg(pl + o11[k]);
+            }
+            const float df = __ldg(a.dfeatures + (size_t)gi * FL + l * FD + lane);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const AxisTap& X = ax[comb_a(k)];
+                const AxisTap& Y = ax[comb_b(k)];
+                s[k] = (X.omf * Y.omf) * v[k][0] + (X.f * Y.omf) * v[k][1] + (X.omf * Y.f) * v[k][2] +
+                       (X.f * Y.f) * v[k][3];
+            }
+            // prefix / suffix products: ds_k = df * prod_{j != k} s_j
+            float pre[6], suf[6];
+            pre[0] = 1.f;
+#pragma unroll
+            for (int k = 1; k < 6; ++k) pre[k] = pre[k - 1] * s[k - 1];
+            suf[5] = 1.f;
+#pragma unroll
+            for (int k = 4; k >= 0; --k) suf[k] = suf[k + 1] * s[k + 1];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int ca = comb_a(k), cb = comb_b(k);
+                const AxisTap& X = ax[ca];
+                const AxisTap& Y = ax[cb];
+                const float ds = df * pre[k] * suf[k];
+                float* gp = a.gplanes[l][k] + lane;
+                // a clamped neighbour carries weight 0 and is skipped
+                atomicAdd(gp + o00[k], (X.omf * Y.omf) * ds);
+                if (X.f != 0.f) atomicAdd(gp + o01[k], (X.f * Y.omf) * ds);
+                if (Y.f != 0.f) atomicAdd(gp + o10[k], (X.omf * Y.f) * ds);
+                if (X.f != 0.f && Y.f != 0.f) atomicAdd(gp + o11[k], (X.f * Y.f) * ds);
+                // d(sample)/d(ix), d(sample)/d(iy)
+                const float dsx = (v[k][1] - v[k][0]) * Y.omf + (v[k][3] - v[k][2]) * Y.f;
+                const float dsy = (v[k][2] - v[k][0]) * X.omf + (v[k][3] - v[k][1]) * X.f;
+                if (ca < 3) dph[ca] += ds * dsx * X.g;
+                if (cb < 3) dph[cb] += ds * dsy * Y.g;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dph[c] += __shfl_xor_sync(0xffffffffu, dph[c], o);
+        }
+        if (lane < 3) a.d_xyz[(size_t)gi * 3 + lane] += dph[lane] * n.inv_span2[lane];
+    }
+}
+
+// sum the per-CTA partial Linear gradients: one thread per gradient element
 struct ReduceSeg { float* dst; int off; int count; };
 struct ReduceArgs { ReduceSeg seg[32]; int nseg; const float* partial; int stride; int nparts; };
 __global__ void __launch_bounds__(256) deform_reduce_kernel(ReduceArgs r) {
-    const ReduceSeg sg = r.seg[blockIdx.x];
-    for (int i = threadIdx.x; i < sg.count; i += blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < r.nparts; ++p) s += r.partial[(size_t)p * r.stride + sg.off + i];
-        sg.dst[i] = s;
+    const ReduceSeg sg = r.seg[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sg.count) return;
+    const float* p = r.partial + sg.off + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int q = 0;
+    for (; q + 4 <= r.nparts; q += 4) {      // four independent loads in flight
+        s0 += p[(size_t)q * r.stride];
+        s1 += p[(size_t)(q + 1) * r.stride];
+        s2 += p[(size_t)(q + 2) * r.stride];
+        s3 += p[(size_t)(q + 3) * r.stride];
     }
+    for (; q < r.nparts; ++q) s0 += p[(size_t)q * r.stride];
+    sg.dst[i] = (s0 + s1) + (s2 + s3);
 }
 
 }  // namespace s3g

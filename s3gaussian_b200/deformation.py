@@ -67,20 +67,6 @@ _HEAD_FLAG = {"pos_deform": "no_dx", "scales_deform": "no_ds", "rotations_deform
               "opacity_deform": "no_do", "shs_deform": "no_dshs"}
 
 
-def _declare(lib):
-    if getattr(lib, "_deform_declared", False):
-        return
-    V, F, I = C.c_void_p, C.c_float, C.c_int
-    lib.s3g_deform_forward.restype = I
-    lib.s3g_deform_forward.argtypes = [C.POINTER(CNet), I] + [V] * 5 + [F, V, I] + [V] * 8 + [V]
-    lib.s3g_deform_workspace_bytes.restype = C.c_size_t
-    lib.s3g_deform_workspace_bytes.argtypes = [C.POINTER(CNet)]
-    lib.s3g_deform_backward.restype = I
-    lib.s3g_deform_backward.argtypes = ([C.POINTER(CNet), I] + [V] * 5 + [F, V, I] + [V] * 8 + [V] * 5 +
-                                        [C.POINTER(CNetGrads), V, V])
-    lib._deform_declared = True
-
-
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -282,7 +268,6 @@ class _DeformFront(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, time, campos, sh_degree, raw_outputs, xyz, scaling, rotation, opacity, shs, *params):
         lib = _lib.load()
-        _declare(lib)
         if not xyz.is_cuda:
             raise RuntimeError("s3gaussian_b200 has no CPU path: xyz must be a CUDA tensor")
         dev = xyz.device
@@ -303,11 +288,12 @@ class _DeformFront(torch.autograd.Function):
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         means, sc_o, ro_o, op_o = e(P, 3), e(P, 3), e(P, 4), e(P, 1)
         colors, dx, dshs, feat = e(P, 3), e(P, 3), e(P, 16, 3), e(P, 3)
+        features = e(P, 32 * len(module.deformation_net.grid.grids))     # sampler -> decoder hand-over, kept for backward
         campos_ = campos.detach().to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             _lib.check(lib.s3g_deform_forward(C.byref(cnet), P, _p(xyz_), _p(sc_), _p(ro_), _p(op_), _p(shs_),
                                               float(time), _p(campos_), int(sh_degree), _p(means), _p(sc_o),
-                                              _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat),
+                                              _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat), _p(features),
                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                        "s3g_deform_forward")
         if raw_outputs:
@@ -317,15 +303,14 @@ class _DeformFront(torch.autograd.Function):
                 raise NotImplementedError("forward_dynamic with scale/rotation/opacity heads: use render_front()")
             sc_o, ro_o, op_o = sc_.clone(), ro_.clone(), op_.clone()
         ctx.module, ctx.time, ctx.sh_degree, ctx.raw, ctx.names = module, float(time), int(sh_degree), raw_outputs, names
-        ctx.save_for_backward(xyz_, sc_, ro_, op_, shs_, campos_, *[p.detach() for p in params])
+        ctx.save_for_backward(xyz_, sc_, ro_, op_, shs_, campos_, features, *[p.detach() for p in params])
         return means, sc_o, ro_o, op_o, colors, dx, dshs, feat
 
     @staticmethod
     def backward(ctx, g_means, g_sc, g_ro, g_op, g_col, g_dx, g_dshs, g_feat):
         lib = _lib.load()
-        _declare(lib)
         module = ctx.module
-        xyz, sc, ro, op, shs, campos, *params = ctx.saved_tensors
+        xyz, sc, ro, op, shs, campos, features, *params = ctx.saved_tensors
         dev = xyz.device
         P = xyz.shape[0]
         byname = dict(zip(ctx.names, params))
@@ -344,10 +329,10 @@ class _DeformFront(torch.autograd.Function):
                 pgrads[n] = torch.empty_like(p)
         cnet, cg = CNet(), CNetGrads()
         module._fill(cnet, byname, grads=(cg, pgrads))
-        ws = torch.empty(int(lib.s3g_deform_workspace_bytes(C.byref(cnet))), dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(lib.s3g_deform_workspace_bytes(C.byref(cnet), P)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.s3g_deform_backward(C.byref(cnet), P, _p(xyz), _p(sc), _p(ro), _p(op), _p(shs), ctx.time,
-                                               _p(campos), ctx.sh_degree, _p(g_means), _p(g_sc), _p(g_ro), _p(g_op),
+                                               _p(campos), ctx.sh_degree, _p(features), _p(g_means), _p(g_sc), _p(g_ro), _p(g_op),
                                                _p(g_col), _p(g_dx), _p(g_dshs), _p(g_feat), _p(d_xyz), _p(d_sc),
                                                _p(d_ro), _p(d_op), _p(d_shs), C.byref(cg), _p(ws),
                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),

@@ -1,0 +1,133 @@
+"""View-parallel data parallelism for the render path.
+
+The reference has no distributed code: it renders a batch of cameras in a sequential
+loop and combines them at the loss (train.py:372-392).  Each view's forward+backward is
+independent given replicated parameters, so the batch shards by CAMERA: one process per
+GPU (torch.distributed, NCCL over NVLink/NVSwitch), rank r renders views r, r+G, ...,
+and the only exchange is
+
+  * one all-reduce (SUM) of the flat fp32 gradient bucket per step: per-Gaussian grads
+    (59 floats = 236 B each) + the 35.8 M deformation parameters (143 MB);
+  * the densify statistics (viewspace-gradient norm accumulates with SUM, radii with MAX,
+    visibility with OR; gaussian_model.py:693-695, train.py:489-499);
+  * a broadcast of the Gaussian tensors after rank 0 densifies/prunes
+    (gaussian_model.py:496-561 samples with torch.normal, so ranks would diverge).
+
+Host-side logic only; works with any backend (the CPU tests run it over gloo).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """(rank, world, local_rank).  Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun)."""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device(f"cuda:{local}")
+        dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def shard_views(views: Sequence, rank: int, world: int) -> list:
+    """Views of one step's batch owned by `rank` (round-robin; 8 views / 8 GPUs = 1 each)."""
+    return [v for i, v in enumerate(views) if i % world == rank]
+
+
+class GradBucket:
+    """Flat fp32 bucket over a fixed parameter list: one collective per step.
+
+    `attach()` points every p.grad at its slice of the bucket, so autograd accumulates the
+    local gradients straight into it (no gather copy); `zero()` clears it; `all_reduce()`
+    sums it over the ranks in place (optionally averaging)."""
+
+    def __init__(self, params: Iterable[torch.Tensor]):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("GradBucket needs at least one parameter")
+        dev, dt = self.params[0].device, torch.float32
+        self.offsets, n = [], 0
+        for p in self.params:
+            if p.dtype != dt or p.device != dev:
+                raise ValueError("all bucket parameters must be float32 on one device")
+            self.offsets.append(n)
+            n += p.numel()
+        self.flat = torch.zeros(n, dtype=dt, device=dev)
+        self.attach()
+
+    def attach(self):
+        for p, o in zip(self.params, self.offsets):
+            g = self.flat[o:o + p.numel()]
+            if p.is_contiguous():
+                p.grad = g.view(p.shape)
+            else:   # channels-last planes: same memory order as the parameter
+                p.grad = g.as_strided(p.shape, p.stride())
+
+    def zero(self):
+        self.flat.zero_()
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def all_reduce(self, average: bool = False):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat.div_(dist.get_world_size())
+        return self.flat
+
+
+def sync_densify_stats(xyz_gradient_accum, denom, max_radii2D, visibility=None):
+    """Make the densification statistics identical on every rank (train.py:489-499):
+    the gradient-norm accumulator and its denominator add up, the screen radii take the max."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM)
+    dist.all_reduce(denom, op=dist.ReduceOp.SUM)
+    dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX)
+    if visibility is not None:
+        v = visibility.to(torch.int32)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        visibility.copy_(v.bool())
+
+
+def broadcast_gaussians(tensors: dict, src: int = 0) -> dict:
+    """After `src` densified / pruned: ship the new point count, then every per-Gaussian tensor
+    (and whatever else is in `tensors`, e.g. Adam moments).  Non-source ranks get NEW tensors of
+    the right size; returns the dict to install."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return tensors
+    rank = dist.get_rank()
+    names = sorted(tensors)
+    dev = tensors[names[0]].device
+    out = {}
+    for k in names:
+        t = tensors[k]
+        shape = torch.tensor(list(t.shape) + [-1] * (8 - t.dim()), dtype=torch.int64, device=dev)
+        dist.broadcast(shape, src)
+        dims = [int(v) for v in shape.tolist() if v >= 0]
+        buf = t.contiguous() if rank == src else torch.empty(dims, dtype=t.dtype, device=dev)
+        dist.broadcast(buf, src)
+        out[k] = buf
+    return out
+
+
+def max_over_ranks(value: float, device) -> float:
+    """device-timed milliseconds -> the slowest rank's (what a step costs)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])

@@ -75,3 +75,39 @@ def decode_binning(buf, R):
 def decode_image(buf, N):
     return _carve(buf, [("accum_alpha", np.float32, N), ("n_contrib", np.uint32, N),
                         ("ranges", np.uint32, 2 * N)])
+
+
+# ---- the reference's PyTorch HexPlane / deformation module (oracle/_ref/s3g_ref) ----
+def deform_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "scene", "deformation.py"))
+
+
+def load_ref_deform():
+    """(deform_network class, eval_sh) of the UNMODIFIED reference, imported from the git-ignored
+    install dir; `tkinter` (scene/deformation.py:5) and the scene/utils package __init__s are
+    stand-ins because the path never touches what they would import."""
+    import types
+    base = os.path.join(REF_DIR, "s3g_ref")
+    sys.modules.setdefault("tkinter", types.ModuleType("tkinter")).W = None
+    for name in ("scene", "utils"):
+        if name not in sys.modules or not getattr(sys.modules[name], "__path__", None) or \
+                base not in str(sys.modules[name].__path__):
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(base, name)]
+            sys.modules[name] = m
+    from scene.deformation import deform_network
+    from utils.sh_utils import eval_sh
+    return deform_network, eval_sh
+
+
+def ref_deform_args(resolution, multires, **flags):
+    from argparse import Namespace
+    d = dict(net_width=64, timebase_pe=4, defor_depth=1, posebase_pe=10, scale_rotation_pe=2, opacity_pe=2,
+             timenet_width=64, timenet_output=32, bounds=1.6, plane_tv_weight=0.0001, time_smoothness_weight=0.01,
+             l1_time_planes=0.0001,
+             kplanes_config={"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": 32,
+                             "resolution": list(resolution)},
+             multires=list(multires), no_dx=False, no_grid=False, no_ds=True, no_dr=True, no_do=True, no_dshs=False,
+             feat_head=True, empty_voxel=False, grid_pe=0, static_mlp=False, apply_rotation=False)
+    d.update(flags)
+    return Namespace(**d)

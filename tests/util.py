@@ -134,3 +134,53 @@ def relerr(a, b):
 def seeded_grads(d, seed=1):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(3, d["H"], d["W"], generator=g), torch.randn(1, d["H"], d["W"], generator=g))
+
+
+# ---- the reference's fine-stage render() code path, assembled from ITS OWN modules ----------
+class RefFineStack:
+    """gaussian_renderer/__init__.py:89-166 with the reference's deform_network (PyTorch), activations,
+    eval_sh and CUDA rasterizer, all from oracle/_ref.  Used as the checker and as bench.py's reference arm
+    for the fine-stage workload."""
+
+    def __init__(self, cloud, state, dev, resolution, multires):
+        import ref_ext
+        from s3gaussian_b200 import synthetic as syn
+        self.ref = ref_ext.load()
+        deform_network, self.eval_sh = ref_ext.load_ref_deform()
+        net = deform_network(ref_ext.ref_deform_args(resolution, multires))
+        net.deformation_net.set_aabb(*[list(a) for a in syn.WAYMO_AABB])
+        net.load_state_dict(state, strict=False)
+        self.net = net.to(dev)
+        self.dev = dev
+        T = lambda t: t.to(dev).clone().requires_grad_(True)
+        self.xyz, self.scaling, self.rotation, self.opacity = T(cloud.xyz), T(cloud.scaling), T(cloud.rotation), T(cloud.opacity)
+        self.f_dc, self.f_rest = T(cloud.features_dc), T(cloud.features_rest)
+        self.P = cloud.xyz.shape[0]
+
+    def leaves(self):
+        return [self.xyz, self.scaling, self.rotation, self.opacity, self.f_dc, self.f_rest] + list(self.net.parameters())
+
+    def render(self, cam, bg, render_feat=True):
+        dev, P = self.dev, self.P
+        shs = torch.cat((self.f_dc, self.f_rest), dim=1)
+        t = torch.full((P, 1), float(cam.time), device=dev)
+        m3, sc, ro, op, shf, dx, feat, dshs = self.net(self.xyz, self.scaling, self.rotation, self.opacity, shs, t)
+        s_a, r_a, o_a = torch.exp(sc), torch.nn.functional.normalize(ro), torch.sigmoid(op)
+        campos = cam.camera_center.to(dev)
+        dirn = self.xyz - campos.repeat(P, 1)
+        dirn = dirn / dirn.norm(dim=1, keepdim=True)
+        colors = torch.clamp_min(self.eval_sh(3, shf.transpose(1, 2).view(-1, 3, 16), dirn) + 0.5, 0.0)
+        rs = self.ref.GaussianRasterizationSettings(
+            image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg,
+            scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(dev), projmatrix=cam.full_proj_transform.to(dev),
+            sh_degree=3, campos=campos, prefiltered=False, debug=False)
+        rast = self.ref.GaussianRasterizer(rs)
+        m2d = torch.zeros_like(self.xyz, requires_grad=True)
+        img, radii, dep = rast(means3D=m3, means2D=m2d, shs=None, colors_precomp=colors, opacities=o_a, scales=s_a,
+                               rotations=r_a, cov3D_precomp=None)
+        out = {"render": img, "radii": radii, "depth": dep, "dx": dx, "dshs": dshs, "viewspace_points": m2d}
+        if render_feat:
+            img2, _, _ = rast(means3D=m3, means2D=m2d, shs=None, colors_precomp=feat, opacities=o_a, scales=s_a,
+                              rotations=r_a, cov3D_precomp=None)
+            out["feat"] = img2
+        return out

@@ -226,6 +226,11 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
                         float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
                         const s3g_deform_net_grads* grads, void* workspace, void* stream);
 
+/* ---- tcgen05 building-block self-test (csrc/umma_test.cu) -----------------
+ * D[128,N] = A[128,K] * B[N,K]^T on the 5th-gen tensor cores (kind::tf32, accumulators in TMEM),
+ * single pass or 3xTF32.  K % 8 == 0, K <= 128, N % 16 == 0, N <= 64.  Device pointers. */
+int s3g_umma_selftest(const float* A, const float* B, float* D, int K, int N, int three_pass, void* stream);
+
 /* ---- per-stage device timing (bench.py roofline leg) ----------------------
  * When enabled, forward/backward bracket every kernel stage with cudaEvents on
  * the caller's stream.  s3g_profile_read() synchronises those events and copies

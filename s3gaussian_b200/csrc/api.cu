@@ -479,11 +479,30 @@ int to_dnet(const s3g_deform_net* n, DNet& d) {
         return fail(S3G_ERR_ARG, "deform: incomplete dino head");
     return S3G_OK;
 }
+// weight matrices in the order one tile consumes them (see WPipe)
+void build_wseq(const DNet& d, bool backward, WSeq& q) {
+    q.count = 0;
+    auto add = [&](const float* W, int N, int K) { q.W[q.count] = W; q.N[q.count] = (short)N; q.K[q.count] = (short)K; ++q.count; };
+    const int KF = FD * d.L;
+    add(d.w_feat, 64, KF);
+    const Head2* small[4] = {&d.pos, &d.scl, &d.rot, &d.opa};
+    for (const Head2* h : small)
+        if (h->w1) { add(h->w1, 64, 64); if (backward) add(h->w1, 64, 64); }
+    if (d.shs.w1) {
+        add(d.shs.w1, 64, 64); add(d.shs.w2, 48, 64);
+        if (backward) { add(d.shs.w2, 48, 64); add(d.shs.w1, 64, 64); }
+    }
+    if (d.w_d0) {
+        add(d.w_d0, 64, 64); add(d.w_d2, 64, 64);
+        if (backward) { add(d.w_d2, 64, 64); add(d.w_d0, 64, 64); }
+    }
+    if (backward) add(d.w_feat, 64, KF);
+}
 int deform_grid(int ntiles) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int g = 2 * sms;
+    const int g = sms;      // one persistent CTA per SM (shared memory: weights double-buffered)
     return ntiles < g ? ntiles : g;
 }
 }  // namespace
@@ -510,6 +529,7 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
     a.campos = campos; a.time = time; a.sh_degree = sh_degree;
     a.o_means = means3D; a.o_scales = scales_act; a.o_rot = rot_act; a.o_opacity = opacity_act;
     a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat; a.features = features;
+    build_wseq(a.net, false, a.wseq);
     {
         SampleArgs sa;
         sa.net = a.net; sa.P = P; sa.xyz = xyz; sa.time = time; sa.features = features;
@@ -599,6 +619,7 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
             if (!a.gplanes[l][k]) return fail(S3G_ERR_ARG, "deform_backward: null plane gradient");
         }
     make_offsets(d, a.off);
+    build_wseq(d, true, a.wseq);
     a.partial = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     a.features = features;
     a.dfeatures = a.partial + (size_t)kMaxBwdGrid * a.off.total;

@@ -80,17 +80,62 @@ __device__ __forceinline__ void stage_weight(const float* __restrict__ Wg, int N
     }
 }
 
+// ---- double-buffered weight staging -------------------------------------------------
+// Every dense layer of a tile reads its weight matrix from shared memory.  Staging it at the
+// top of the layer exposes one L2 round trip per layer (~1.5 us x ~10-20 layers per tile,
+// more than the MMA time); instead the NEXT layer's weights are fetched with cp.async into the
+// other buffer while the current layer computes.  The per-tile sequence of weights is fixed, so
+// the host passes it in (WSeq) and the pipe walks it cyclically.
+struct WSeq {
+    const float* W[28];
+    short N[28], K[28];
+    int count;
+};
+__device__ __forceinline__ void cp_async16_w(void* smem, const void* gmem) {
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+struct WPipe {
+    float* buf[2];
+    int cur, wi;
+    const WSeq* seq;
+    __device__ __forceinline__ void prefetch(int i, float* dst) const {
+        const int K = seq->K[i], N = seq->N[i], WS = K + 4, k4n = K >> 2;
+        const float* Wg = seq->W[i];
+        for (int e = threadIdx.x; e < N * k4n; e += DTHREADS) {
+            const int n = e / k4n, k4 = e - n * k4n;
+            cp_async16_w(dst + n * WS + 4 * k4, Wg + (size_t)n * K + 4 * k4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void start() {   // kernel prologue
+        cur = 0; wi = 0;
+        prefetch(0, buf[0]);
+    }
+    // weights of layer `wi` are ready in the returned buffer; the next layer's are in flight
+    __device__ __forceinline__ float* acquire() {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        float* mine = buf[cur];
+        const int nxt = (wi + 1 == seq->count) ? 0 : wi + 1;
+        if (seq->W[nxt] != seq->W[wi]) {
+            prefetch(nxt, buf[cur ^ 1]);
+            cur ^= 1;
+        }
+        wi = nxt;
+        return mine;
+    }
+};
+
 // out[g][n] = act_out( sum_k act_in(in[g][k]) * W[n][k] + b[n] ),  g < 64, n < N (N = 64 or 48).
 // 8 warps: (warp & 3) picks 16 rows, (warp >> 2) picks half of the columns.
 // sIn / sOut / sW are distinct smem regions; ends with a __syncthreads().
 template <int K, int N, bool RELU_IN, bool RELU_OUT>
-__device__ __forceinline__ void tile_linear(const float* sIn, int inStride, const float* __restrict__ Wg,
-                                            const float* __restrict__ bg, float* sW, float* sOut,
-                                            int outStride) {
+__device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPipe& pipe,
+                                            const float* __restrict__ bg, float* sOut, int outStride) {
     constexpr int WS = K + 4;
     constexpr int NTW = N / 16;          // n-tiles (of 8) per warp
-    stage_weight<K>(Wg, N, sW);
-    __syncthreads();
+    const float* sW = pipe.acquire();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = (warp & 3) * 16;
     const int c0 = (warp >> 2) * (N / 2);
@@ -244,6 +289,7 @@ struct DeformFwdArgs {
     int sh_degree;
     float *o_means, *o_scales, *o_rot, *o_opacity, *o_colors, *o_dx, *o_dshs, *o_feat;
     float* features;     // [P][32L] written by hexplane_sample_kernel, read by the decoder tiles
+    WSeq wseq;           // weight matrices in the order the tile uses them
 };
 
 // ---- stage 1: HexPlane sampling, one warp per Gaussian, high occupancy ---------------
@@ -299,21 +345,21 @@ struct DeformSmem {
         A = F;                            // [64][HS]
         B = F + DT * HS;                  // [64][HS]   (needs 2*HS <= FS, i.e. L >= 4, else separate: see host sizing)
         H = base + DT * (FS > 2 * HS ? FS : 2 * HS);      // [64][HS]
-        W = H + DT * HS;                  // [64][max(FS,HS)] weight staging
-        S = W + HWID * (FS > HS ? FS : HS);               // [64][16] small head outputs
+        W = H + DT * HS;                  // 2 x [64][max(FS,HS)] weight staging (double-buffered)
+        S = W + 2 * HWID * (FS > HS ? FS : HS);           // [64][16] small head outputs
         Dsh = S + DT * 16;                // [64][52] dshs / shs_final
         X = Dsh + DT * 52;                // [64][4] xyz of the tile
     }
     __host__ __device__ static size_t floats(int L) {
         const int FS = FD * L + 4;
-        return (size_t)DT * (FS > 2 * HS ? FS : 2 * HS) + DT * HS + HWID * (FS > HS ? FS : HS) + DT * 16 + DT * 52 + DT * 4;
+        return (size_t)DT * (FS > 2 * HS ? FS : 2 * HS) + DT * HS + 2 * HWID * (FS > HS ? FS : HS) + DT * 16 + DT * 52 + DT * 4;
     }
 };
 // columns of the small-output tile S
 constexpr int S_DX = 0, S_DS = 3, S_DR = 6, S_DO = 10, S_FEAT = 11;
 
 template <int LT>   // LT = 4: compile-time level count (K of the first layer = 128); 0: generic via K=32*L switch
-__global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdArgs a) {
+__global__ void __launch_bounds__(DTHREADS, 1) deform_forward_kernel(const __grid_constant__ DeformFwdArgs a) {
     extern __shared__ __align__(16) float s_dyn[];
     const DNet& n = a.net;
     const int L = n.L;
@@ -321,6 +367,11 @@ __global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdAr
     DeformSmem sm(s_dyn, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntiles = (a.P + DT - 1) / DT;
+    WPipe pipe;
+    pipe.seq = &a.wseq;
+    pipe.buf[0] = sm.W;
+    pipe.buf[1] = sm.W + HWID * (FS > HS ? FS : HS);
+    pipe.start();
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * DT;
@@ -335,42 +386,42 @@ __global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdAr
         __syncthreads();
         // ---- 2. decoder ------------------------------------------------------
         // h = feature_out(f)
-        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         // zero the small outputs (disabled heads contribute 0)
         for (int i = tid; i < DT * 16; i += DTHREADS) sm.S[i] = 0.f;
         __syncthreads();
         if (n.pos.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.pos.w1, n.pos.b1, sm.W, sm.A, HS);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.pos.b1, sm.A, HS);
             tile_small_out(sm.A, HS, n.pos.w2, n.pos.b2, 3, sm.S, 16, S_DX);
         }
         if (n.scl.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.scl.w1, n.scl.b1, sm.W, sm.B, HS);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.scl.b1, sm.B, HS);
             tile_small_out(sm.B, HS, n.scl.w2, n.scl.b2, 3, sm.S, 16, S_DS);
         }
         __syncthreads();
         if (n.rot.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.rot.w1, n.rot.b1, sm.W, sm.A, HS);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.rot.b1, sm.A, HS);
             tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.S, 16, S_DR);
         }
         if (n.opa.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.opa.w1, n.opa.b1, sm.W, sm.B, HS);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.opa.b1, sm.B, HS);
             tile_small_out(sm.B, HS, n.opa.w2, n.opa.b2, 1, sm.S, 16, S_DO);
         }
         __syncthreads();
         if (n.shs.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.shs.w1, n.shs.b1, sm.W, sm.A, HS);
-            tile_linear<64, 48, false, false>(sm.A, HS, n.shs.w2, n.shs.b2, sm.W, sm.Dsh, 52);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
+            tile_linear<64, 48, false, false>(sm.A, HS, pipe, n.shs.b2, sm.Dsh, 52);
         } else {
             for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dsh[i] = 0.f;
             __syncthreads();
         }
         if (n.w_d0) {   // dino head: Linear, ReLU, Linear, ReLU, Linear - no leading ReLU (deformation.py:70-76)
-            tile_linear<64, 64, false, true>(sm.H, HS, n.w_d0, n.b_d0, sm.W, sm.A, HS);
-            tile_linear<64, 64, false, true>(sm.A, HS, n.w_d2, n.b_d2, sm.W, sm.B, HS);
+            tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
+            tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
             tile_small_out(sm.B, HS, n.w_d4, n.b_d4, 3, sm.S, 16, S_FEAT);
         }
         __syncthreads();
@@ -435,13 +486,11 @@ __global__ void __launch_bounds__(DTHREADS, 2) deform_forward_kernel(DeformFwdAr
 // i.e. the transposed product used to push deltas back through a Linear.
 enum { TL_ASSIGN = 0, TL_ASSIGN_MASK = 1, TL_ACCUM = 2, TL_ACCUM_MASK = 3 };
 template <int K, int N, int MODE>
-__device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, const float* __restrict__ Wg,
-                                              float* sW, float* sOut, int outStride, const float* sMask,
-                                              int maskStride) {
+__device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WPipe& pipe, float* sOut,
+                                              int outStride, const float* sMask, int maskStride) {
     constexpr int WS = K + 4;
     constexpr int NTW = K / 16;          // output n-tiles (of 8) per warp
-    stage_weight<K>(Wg, N, sW);
-    __syncthreads();
+    const float* sW = pipe.acquire();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = (warp & 3) * 16;
     const int c0 = (warp >> 2) * (K / 2);
@@ -572,6 +621,7 @@ struct DeformBwdArgs {
     const float* features;   // [P][32L] from the forward
     float* dfeatures;        // [P][32L] dL/d(features), consumed by hexplane_scatter_kernel
     GradOff off;
+    WSeq wseq;
 };
 
 struct DeformBwdSmem {
@@ -588,13 +638,13 @@ struct DeformBwdSmem {
         D1 = A + DT * AB;
         D2 = D1 + DT * HS;
         Dout = D2 + DT * HS;           // [64][52]
-        W = Dout + DT * 52;            // [64][max(FS,HS)]
-        G = W + HWID * (FS > HS ? FS : HS);   // [64][16] per-Gaussian scalars (small deltas)
+        W = Dout + DT * 52;            // 2 x [64][max(FS,HS)] (double-buffered weight staging)
+        G = W + 2 * HWID * (FS > HS ? FS : HS);   // [64][16] per-Gaussian scalars (small deltas)
     }
     __host__ __device__ static size_t floats(int L) {
         const int FS = FD * L + 4;
         const int AB = (FS > 2 * HS ? FS : 2 * HS);
-        return (size_t)DT * 4 + DT * FS + 2 * DT * HS + DT * AB + 2 * DT * HS + DT * 52 + HWID * (FS > HS ? FS : HS) + DT * 16;
+        return (size_t)DT * 4 + DT * FS + 2 * DT * HS + DT * AB + 2 * DT * HS + DT * 52 + 2 * HWID * (FS > HS ? FS : HS) + DT * 16;
     }
 };
 
@@ -602,15 +652,15 @@ __device__ __forceinline__ float ldz(const float* p, size_t i) { return p ? p[i]
 
 template <int KF>   // KF = 32*L
 __device__ __forceinline__ void feat_layers_bwd(const DeformBwdSmem& sm, const DNet& n, float* part, const GradOff& off,
-                                                int FS) {
+                                                int FS, WPipe& pipe) {
     // dW0 += DH^T F ; db0 ; DF = DH W0  (DF aliases A|B)
     dw_accum<64, KF, false>(sm.DH, HS, sm.F, FS, part + off.w_feat, part + off.b_feat);
     __syncthreads();
-    tile_linear_T<KF, 64, TL_ASSIGN>(sm.DH, HS, n.w_feat, sm.W, sm.A, FS, nullptr, 0);
+    tile_linear_T<KF, 64, TL_ASSIGN>(sm.DH, HS, pipe, sm.A, FS, nullptr, 0);
 }
 
 template <int LT>
-__global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdArgs a) {
+__global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __grid_constant__ DeformBwdArgs a) {
     extern __shared__ __align__(16) float s_dyn[];
     const DNet& n = a.net;
     const int L = n.L;
@@ -620,6 +670,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
     const int ntiles = (a.P + DT - 1) / DT;
     float* part = a.partial + (size_t)blockIdx.x * a.off.total;
     for (int i = tid; i < a.off.total; i += DTHREADS) part[i] = 0.f;
+    WPipe pipe;
+    pipe.seq = &a.wseq;
+    pipe.buf[0] = sm.W;
+    pipe.buf[1] = sm.W + HWID * (FS > HS ? FS : HS);
+    pipe.start();
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -633,11 +688,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
         // ---- features of the tile (saved by the forward), hidden recomputed -------
         tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
         __syncthreads();
-        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
-        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, n.w_feat, n.b_feat, sm.W, sm.H, HS);
+        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
 
         // ---- per-Gaussian activation backward -> small deltas in G[g][0..10] ----
         //  G: [0..2] d(dx) , [3..5] d(ds), [6..9] d(dr), [10] d(do)
@@ -657,18 +712,18 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
 
         // ---- pos head ------------------------------------------------------------
         if (n.pos.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, n.pos.w1, n.pos.b1, sm.W, sm.A, HS);
+            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.pos.b1, sm.A, HS);
             if (tid < DT * 4) sm.Dout[tid] = sm.G[(tid >> 2) * 16 + (tid & 3)] * ((tid & 3) < 3 ? 1.f : 0.f);
             __syncthreads();
             small_head_backward(sm.Dout, 3, sm.A, HS, n.pos.w2, part + a.off.pos[2], part + a.off.pos[3], sm.D1, HS);
             dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.pos[0], part + a.off.pos[1]);
-            tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.pos.w1, sm.W, sm.DH, HS, sm.H, HS);
+            tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
         }
         // ---- scales head: scales_act = exp(scales + ds) ---------------------------
         {
             const bool on = n.scl.w1 != nullptr;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, n.scl.w1, n.scl.b1, sm.W, sm.A, HS);
+                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.scl.b1, sm.A, HS);
                 tile_small_out(sm.A, HS, n.scl.w2, n.scl.b2, 3, sm.G, 16, 11);     // ds -> G[11..13]
                 __syncthreads();
             }
@@ -686,14 +741,14 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
             if (on) {
                 small_head_backward(sm.Dout, 3, sm.A, HS, n.scl.w2, part + a.off.scl[2], part + a.off.scl[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.scl[0], part + a.off.scl[1]);
-                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.scl.w1, sm.W, sm.DH, HS, sm.H, HS);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
         }
         // ---- rotation head: rot_act = normalize(rot + dr) --------------------------
         {
             const bool on = n.rot.w1 != nullptr;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, n.rot.w1, n.rot.b1, sm.W, sm.A, HS);
+                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.rot.b1, sm.A, HS);
                 tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.G, 16, 11);     // dr -> G[11..14]
                 __syncthreads();
             }
@@ -729,14 +784,14 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
             if (on) {
                 small_head_backward(sm.Dout, 4, sm.A, HS, n.rot.w2, part + a.off.rot[2], part + a.off.rot[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.rot[0], part + a.off.rot[1]);
-                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.rot.w1, sm.W, sm.DH, HS, sm.H, HS);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
         }
         // ---- opacity head: opacity_act = sigmoid(opacity + do) ---------------------
         {
             const bool on = n.opa.w1 != nullptr;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, n.opa.w1, n.opa.b1, sm.W, sm.A, HS);
+                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.opa.b1, sm.A, HS);
                 tile_small_out(sm.A, HS, n.opa.w2, n.opa.b2, 1, sm.G, 16, 11);     // do -> G[11]
                 __syncthreads();
             }
@@ -755,15 +810,15 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
             if (on) {
                 small_head_backward(sm.Dout, 1, sm.A, HS, n.opa.w2, part + a.off.opa[2], part + a.off.opa[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.opa[0], part + a.off.opa[1]);
-                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.opa.w1, sm.W, sm.DH, HS, sm.H, HS);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
         }
         // ---- shs head + SH->RGB backward ---------------------------------------------
         {
             const bool on = n.shs.w1 != nullptr;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, n.shs.w1, n.shs.b1, sm.W, sm.A, HS);
-                tile_linear<64, 48, false, false>(sm.A, HS, n.shs.w2, n.shs.b2, sm.W, sm.Dout, 52);   // dshs
+                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
+                tile_linear<64, 48, false, false>(sm.A, HS, pipe, n.shs.b2, sm.Dout, 52);   // dshs
             } else {
                 for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dout[i] = 0.f;
                 __syncthreads();
@@ -858,15 +913,15 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
             __syncthreads();
             if (on) {
                 dw_accum<48, 64, false>(sm.Dout, 52, sm.A, HS, part + a.off.shs[2], part + a.off.shs[3]);
-                tile_linear_T<64, 48, TL_ASSIGN_MASK>(sm.Dout, 52, n.shs.w2, sm.W, sm.D1, HS, sm.A, HS);
+                tile_linear_T<64, 48, TL_ASSIGN_MASK>(sm.Dout, 52, pipe, sm.D1, HS, sm.A, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.shs[0], part + a.off.shs[1]);
-                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, n.shs.w1, sm.W, sm.DH, HS, sm.H, HS);
+                tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
         }
         // ---- dino head ------------------------------------------------------------------
         if (n.w_d0) {
-            tile_linear<64, 64, false, true>(sm.H, HS, n.w_d0, n.b_d0, sm.W, sm.A, HS);
-            tile_linear<64, 64, false, true>(sm.A, HS, n.w_d2, n.b_d2, sm.W, sm.B, HS);
+            tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
+            tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
             if (tid < DT * 4) {
                 const int g = tid >> 2, c = tid & 3, gi = g0 + g;
                 sm.Dout[tid] = (c < 3 && gi < a.P) ? ldz(a.g_feat, (size_t)gi * 3 + c) : 0.f;
@@ -874,17 +929,17 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(DeformBwdA
             __syncthreads();
             small_head_backward(sm.Dout, 3, sm.B, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS);
             dw_accum<64, 64, false>(sm.D2, HS, sm.A, HS, part + a.off.d2w, part + a.off.d2b);
-            tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, n.w_d2, sm.W, sm.D1, HS, sm.A, HS);
+            tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, pipe, sm.D1, HS, sm.A, HS);
             dw_accum<64, 64, false>(sm.D1, HS, sm.H, HS, part + a.off.d0w, part + a.off.d0b);
-            tile_linear_T<64, 64, TL_ACCUM>(sm.D1, HS, n.w_d0, sm.W, sm.DH, HS, nullptr, 0);
+            tile_linear_T<64, 64, TL_ACCUM>(sm.D1, HS, pipe, sm.DH, HS, nullptr, 0);
         }
         __syncthreads();
         // ---- feature layer ---------------------------------------------------------------
-        if (LT == 4 || L == 4) feat_layers_bwd<128>(sm, n, part, a.off, FS);
-        else if (L == 1) feat_layers_bwd<32>(sm, n, part, a.off, FS);
-        else if (L == 2) feat_layers_bwd<64>(sm, n, part, a.off, FS);
-        else if (L == 3) feat_layers_bwd<96>(sm, n, part, a.off, FS);
-        else if (L == 8) feat_layers_bwd<256>(sm, n, part, a.off, FS);
+        if (LT == 4 || L == 4) feat_layers_bwd<128>(sm, n, part, a.off, FS, pipe);
+        else if (L == 1) feat_layers_bwd<32>(sm, n, part, a.off, FS, pipe);
+        else if (L == 2) feat_layers_bwd<64>(sm, n, part, a.off, FS, pipe);
+        else if (L == 3) feat_layers_bwd<96>(sm, n, part, a.off, FS, pipe);
+        else if (L == 8) feat_layers_bwd<256>(sm, n, part, a.off, FS, pipe);
         // DF now lives in sm.A with row stride FS: hand it to the scatter kernel, and write the
         // part of d_xyz that does not go through the planes (identity path + SH view direction)
         tile_rows_store(a.dfeatures, g0, a.P, FD * L, sm.A, FS);

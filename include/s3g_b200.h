@@ -210,7 +210,10 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
                        const float* rotations, const float* opacity, const float* shs, float time,
                        const float* campos, int sh_degree,
                        float* means3D, float* scales_act, float* rot_act, float* opacity_act,
-                       float* colors, float* dx, float* dshs, float* feat, float* features, void* stream);
+                       float* colors, float* dx, float* dshs, float* feat, float* features,
+                       void* workspace, void* stream);
+/* bytes of `workspace` for s3g_deform_forward (tensor-core-ready copies of the Linear weights) */
+size_t s3g_deform_forward_workspace_bytes(const s3g_deform_net* net);
 
 /* Backward of the above.  g_* are dL/d(output) (NULL = zero).  Writes dL/d(raw inputs)
  * [P,*] in full, overwrites the Linear gradients in `grads` and accumulates the plane

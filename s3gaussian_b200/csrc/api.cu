@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "composite.cuh"
 #include "deform.cuh"
+#include "deform_tc.cuh"
 #include "preprocess.cuh"
 #include "radix_sort.cuh"
 
@@ -498,6 +499,25 @@ void build_wseq(const DNet& d, bool backward, WSeq& q) {
     }
     if (backward) add(d.w_feat, 64, KF);
 }
+// prepared-weight table of the tcgen05 decoder
+void build_tc_table(const DNet& d, TcTable& t, TcPrepArgs* prep) {
+    int off = 0;
+    auto put = [&](int id, const float* W, int N, int K) {
+        if (!W) { t.off[id] = -1; t.npad[id] = 0; t.k[id] = 0; if (prep) { prep->W[id] = nullptr; prep->n[id] = 0; } return; }
+        const int np = (N + 15) & ~15;
+        t.off[id] = off; t.npad[id] = np; t.k[id] = K;
+        off += 2 * np * K;
+        if (prep) { prep->W[id] = W; prep->n[id] = N; }
+    };
+    put(TL_FEAT, d.w_feat, 64, FD * d.L);
+    put(TL_POS1, d.pos.w1, 64, 64); put(TL_POS2, d.pos.w1 ? d.pos.w2 : nullptr, 3, 64);
+    put(TL_SCL1, d.scl.w1, 64, 64); put(TL_SCL2, d.scl.w1 ? d.scl.w2 : nullptr, 3, 64);
+    put(TL_ROT1, d.rot.w1, 64, 64); put(TL_ROT2, d.rot.w1 ? d.rot.w2 : nullptr, 4, 64);
+    put(TL_OPA1, d.opa.w1, 64, 64); put(TL_OPA2, d.opa.w1 ? d.opa.w2 : nullptr, 1, 64);
+    put(TL_SHS1, d.shs.w1, 64, 64); put(TL_SHS2, d.shs.w1 ? d.shs.w2 : nullptr, 48, 64);
+    put(TL_D0, d.w_d0, 64, 64); put(TL_D2, d.w_d0 ? d.w_d2 : nullptr, 64, 64); put(TL_D4, d.w_d0 ? d.w_d4 : nullptr, 3, 64);
+    t.total = off;
+}
 int deform_grid(int ntiles) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -513,7 +533,7 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
                        const float* rotations, const float* opacity, const float* shs, float time,
                        const float* campos, int sh_degree, float* means3D, float* scales_act,
                        float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
-                       float* feat, float* features, void* stream_) {
+                       float* feat, float* features, void* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
     if (P == 0) return S3G_OK;
@@ -541,12 +561,28 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
         else hexplane_sample_kernel<0><<<blocks, 256, 0, stream>>>(sa);
         S3G_CUDA(cudaGetLastError(), "hexplane_sample launch");
     }
-    const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
-    const int ntiles = (P + DT - 1) / DT;
-    if (a.net.L == 4) {
-        S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
-        deform_forward_kernel<4><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
+    if (a.net.L <= 4) {
+        // ---- decoder on the 5th-gen tensor cores (tcgen05 / TMEM) ------------------------------
+        if (!workspace) return fail(S3G_ERR_ARG, "deform_forward: null workspace");
+        DeformTcArgs t;
+        t.net = a.net; t.P = P; t.xyz = xyz; t.scales = scales; t.rot = rotations; t.opacity = opacity; t.shs = shs;
+        t.campos = campos; t.sh_degree = sh_degree;
+        t.o_means = means3D; t.o_scales = scales_act; t.o_rot = rot_act; t.o_opacity = opacity_act; t.o_colors = colors;
+        t.o_dx = dx; t.o_dshs = dshs; t.o_feat = feat; t.features = features;
+        TcPrepArgs pp;
+        build_tc_table(a.net, t.tab, &pp);
+        pp.tab = t.tab;
+        pp.dst = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        t.wprep = pp.dst;
+        tc_prep_weights_kernel<<<dim3(8, TL_COUNT), 256, 0, stream>>>(pp);
+        S3G_CUDA(cudaGetLastError(), "tc_prep_weights launch");
+        const size_t smem = (size_t)(2 * TCM * 128 + 2 * 64 * 128) * sizeof(float);
+        S3G_CUDA(cudaFuncSetAttribute(deform_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform tc smem attr");
+        const int ntiles = (P + TCM - 1) / TCM;
+        deform_forward_tc_kernel<<<deform_grid(ntiles), TCM, smem, stream>>>(t);
     } else {
+        const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
+        const int ntiles = (P + DT - 1) / DT;
         S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
         deform_forward_kernel<0><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
     }
@@ -579,6 +615,14 @@ int bwd_grid(int ntiles) {
 }
 constexpr int kMaxBwdGrid = 256;
 }  // namespace
+
+size_t s3g_deform_forward_workspace_bytes(const s3g_deform_net* net) {
+    DNet d;
+    if (to_dnet(net, d) != S3G_OK) return 0;
+    TcTable t;
+    build_tc_table(d, t, nullptr);
+    return (size_t)t.total * sizeof(float) + 512;
+}
 
 size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
     DNet d;

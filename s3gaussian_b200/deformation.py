@@ -290,10 +290,11 @@ class _DeformFront(torch.autograd.Function):
         colors, dx, dshs, feat = e(P, 3), e(P, 3), e(P, 16, 3), e(P, 3)
         features = e(P, 32 * len(module.deformation_net.grid.grids))     # sampler -> decoder hand-over, kept for backward
         campos_ = campos.detach().to(device=dev, dtype=torch.float32).contiguous()
+        fws = torch.empty(int(lib.s3g_deform_forward_workspace_bytes(C.byref(cnet))), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.s3g_deform_forward(C.byref(cnet), P, _p(xyz_), _p(sc_), _p(ro_), _p(op_), _p(shs_),
                                               float(time), _p(campos_), int(sh_degree), _p(means), _p(sc_o),
-                                              _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat), _p(features),
+                                              _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat), _p(features), _p(fws),
                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                        "s3g_deform_forward")
         if raw_outputs:

@@ -253,6 +253,49 @@ int s3g_sort_pairs_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in,
                        uint32_t* keys_out, uint32_t* vals_out,
                        int begin_bit, int end_bit, void* temp, void* stream);
 
+/* ---- training-step kernels either side of render() ------------
+ *
+ * s3g_adam_step       <- torch.optim.Adam(l, lr=0.0, eps=1e-15).step()   scene/gaussian_model.py:189, train.py:520-522
+ *                        (torch/optim/adam.py _multi_tensor_adam: no weight decay, no amsgrad)
+ * s3g_densify_stats   <- max_radii2D update + add_densification_stats    train.py:489-491, scene/gaussian_model.py:693-695
+ * s3g_image_loss_*    <- l1_loss + ssim + compute_depth("l2")            utils/loss_utils.py:20-96, train.py:395-419
+ */
+typedef struct s3g_adam_tensor {
+    float* param;          /* updated in place */
+    const float* grad;
+    float* exp_avg;        /* updated in place */
+    float* exp_avg_sq;     /* updated in place */
+    int64_t numel;
+    double lr;             /* the param group's current lr */
+    int64_t step;          /* state['step'] AFTER this step's increment (>= 1) */
+} s3g_adam_tensor;
+
+/* `tensors` is a HOST array of n descriptors (device pointers inside).  One kernel launch per
+ * 40 tensors.  Tensors with numel == 0 are skipped. */
+int s3g_adam_step(int n, const s3g_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
+
+/* radii i32[P] (max over the step's views), viewspace_grad f32[P,3] (summed over the views);
+ * for radii > 0: max_radii2D = max(max_radii2D, radii); xyz_gradient_accum += |grad[:2]|; denom += 1. */
+int s3g_densify_stats(int P, const float* viewspace_grad, const int* radii, float* xyz_gradient_accum,
+                      float* denom, float* max_radii2D, void* stream);
+
+/* image, gt_image: f32[B,C,H,W] (or C == 0 and NULL: depth term only); depth, gt_depth: f32[B,H,W] or
+ * both NULL (no depth term).
+ * forward: sums (DEVICE double[4]) = {sum|image-gt|, sum ssim_map, sum over valid of
+ *   (clamp(d/max,0,1)-clamp(gt/max,0,1))^2, #valid (0.01 < gt < max_depth)} - the caller forms
+ *   l1 = sums[0]/N, ssim = sums[1]/N, depth_l2 = sums[2]/sums[3] on the device (no host sync) - and
+ *   keeps the SSIM derivative maps in `workspace` (s3g_image_loss_workspace_bytes bytes).
+ * backward: weights (DEVICE float[3]) = dL/d{l1, ssim, depth_l2} as autograd delivers them;
+ *   writes g_image [B,C,H,W] and, with depth, g_depth [B,H,W].  Same workspace and sums. */
+size_t s3g_image_loss_workspace_bytes(int B, int C, int H, int W);
+int s3g_image_loss_forward(int B, int C, int H, int W, const float* image, const float* gt_image,
+                           const float* depth, const float* gt_depth, float max_depth,
+                           double* sums, void* workspace, void* stream);
+int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, const float* gt_image,
+                            const float* depth, const float* gt_depth, float max_depth,
+                            const float* weights, const double* sums, const void* workspace,
+                            float* g_image, float* g_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ ERR_NAMES = {-1: "S3G_ERR_ARG", -2: "S3G_ERR_CUDA", -3: "S3G_ERR_ALLOC", -4: "S3
 _lib = None
 
 # every symbol include/s3g_b200.h declares: (name, restype, argtypes)
-_F, _V, _I, _I64, _SZ = C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_F, _V, _I, _I64, _SZ, _D = C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 SIGNATURES = {
     "s3g_abi_version": (_I, []),
     "s3g_last_error": (C.c_char_p, []),
@@ -47,7 +47,19 @@ SIGNATURES = {
     "s3g_image_bytes": (_SZ, [_I, _I]),
     "s3g_sort_temp_bytes": (_SZ, [_I64]),
     "s3g_sort_pairs_u32": (_I, [_I64, _V, _V, _V, _V, _I, _I, _V, _V]),
+    # training-step kernels; s3g_adam_step takes a host array of AdamTensor (below)
+    "s3g_adam_step": (_I, [_I, _V, _D, _D, _D, _V]),
+    "s3g_densify_stats": (_I, [_I, _V, _V, _V, _V, _V, _V]),
+    "s3g_image_loss_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "s3g_image_loss_forward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V]),
+    "s3g_image_loss_backward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V, _V, _V]),
 }
+
+
+class AdamTensor(C.Structure):
+    """s3g_adam_tensor (include/s3g_b200.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_double), ("step", C.c_int64)]
 
 
 def load():

@@ -111,3 +111,20 @@ def ref_deform_args(resolution, multires, **flags):
              feat_head=True, empty_voxel=False, grid_pe=0, static_mlp=False, apply_rotation=False)
     d.update(flags)
     return Namespace(**d)
+
+
+# ---- the reference's loss functions (oracle/_ref/s3g_ref/utils/loss_utils.py) ----
+def loss_utils_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "utils", "loss_utils.py"))
+
+
+def load_ref_loss_utils():
+    """utils/loss_utils.py of the UNMODIFIED reference (l1_loss, ssim, compute_depth)."""
+    import types
+    base = os.path.join(REF_DIR, "s3g_ref")
+    if "utils" not in sys.modules or base not in str(getattr(sys.modules["utils"], "__path__", "")):
+        m = types.ModuleType("utils")
+        m.__path__ = [os.path.join(base, "utils")]
+        sys.modules["utils"] = m
+    from utils import loss_utils
+    return loss_utils

@@ -234,3 +234,24 @@ def test_render_matches_reference_stack_on_gpu(built_lib):
             assert rel_l2(p.grad, tp[k].grad) < 2e-2, (k, rel_l2(p.grad, tp[k].grad))
             n += 1
     assert n >= 28
+
+
+@pytest.mark.parametrize("K,N", [(64, 64), (128, 64), (64, 48), (64, 16), (8, 16), (128, 32)])
+def test_umma_selftest(K, N, built_lib):
+    """tcgen05 building blocks (csrc/umma.cuh): a 128 x N x K GEMM issued as kind::tf32 UMMAs from
+    canonical K-major smem operands into TMEM, read back with tcgen05.ld.  Single pass has tf32
+    accuracy; the 3-pass split (what the decoder uses) has fp32 accuracy."""
+    import ctypes as C
+    from s3gaussian_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(K * 131 + N)
+    A = torch.randn(128, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    ref = A.double() @ B.double().t()
+    for three, tol in ((0, 3e-3), (1, 2e-6)):
+        D = torch.full((128, N), float("nan"), device=DEV)
+        rc = lib.s3g_umma_selftest(A.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, three,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert rc == 0
+        assert float((D.double() - ref).abs().max() / ref.abs().max()) < tol

@@ -1,0 +1,185 @@
+"""GPU parity of the training-step kernels (run with -m gpu): fused image loss, multi-tensor Adam,
+densification statistics - through the C ABI, against (1) tests/golden/train_*.npz = outputs of the
+REAL reference code, (2) the oracle at sizes the goldens do not cover, (3) torch.optim.Adam itself."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_golden_train as mg                                    # noqa: E402 (input generators only)
+from test_oracle_train import GOLD, LOSS_GOLD, load_loss_case, rel  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("path", LOSS_GOLD, ids=[os.path.basename(p)[11:-4] for p in LOSS_GOLD])
+def test_image_loss_matches_reference_golden(path, built_lib):
+    from s3gaussian_b200 import losses
+    z, img, gt, depth, gt_depth = load_loss_case(path)
+    img = img.to(DEV).requires_grad_(True)
+    depth = depth.to(DEV).requires_grad_(True)
+    l1, ss, dl2 = losses.image_loss_terms(img, gt.to(DEV), depth, gt_depth.to(DEV))
+    loss = l1 + 0.5 * dl2 + 0.2 * (1.0 - ss)
+    loss.backward()
+    assert abs(l1.item() - float(z["l1"])) < 1e-6
+    assert abs(ss.item() - float(z["ssim"])) < 1e-5
+    assert abs(dl2.item() - float(z["depth_l2"])) < 1e-6
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    assert rel(img.grad.cpu(), z["g_image"]) < 1e-4
+    assert rel(depth.grad.cpu(), z["g_depth"]) < 1e-5
+    # the reference-named wrappers give the same numbers one at a time
+    assert abs(losses.l1_loss(img.detach(), gt.to(DEV)).item() - float(z["l1"])) < 1e-6
+    assert abs(losses.ssim(img.detach(), gt.to(DEV)).item() - float(z["ssim"])) < 1e-5
+    assert abs(losses.compute_depth("l2", depth.detach(), gt_depth.to(DEV)).item() - float(z["depth_l2"])) < 1e-6
+
+
+def test_image_loss_full_size_against_oracle_and_properties(built_lib):
+    from oracle import train_oracle as tro
+    from s3gaussian_b200 import losses
+    img, gt, depth, gt_depth = mg.loss_inputs(1, 3, 1280, 1920, 5)
+    img, gt, depth, gt_depth = [t.to(DEV) for t in (img, gt, depth, gt_depth)]
+    x = img.clone().requires_grad_(True)
+    d = depth.clone().requires_grad_(True)
+    ours = losses.training_loss(x, gt, d, gt_depth)
+    ours.backward()
+    xo = img.double().requires_grad_(True)
+    do = depth.double().requires_grad_(True)
+    ref = tro.training_loss(xo, gt.double(), do, gt_depth.double())
+    ref.backward()
+    assert abs(ours.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert rel(x.grad, xo.grad) < 1e-4
+    assert rel(d.grad, do.grad) < 1e-5
+    # ssim(x, x) == 1, zero gradient; l1 symmetric
+    y = gt.clone().requires_grad_(True)
+    l1, ss, _ = losses.image_loss_terms(y, gt)
+    assert abs(ss.item() - 1.0) < 1e-6 and l1.item() == 0.0
+    ss.backward()
+    assert float(y.grad.abs().max()) < 1e-9
+    assert losses.l1_loss(img, gt).item() == losses.l1_loss(gt, img).item()
+
+
+def _groups(ps):
+    groups = {}
+    for (name, _, lr), p in zip(mg.ADAM_SHAPES, ps):
+        groups.setdefault(name, {"params": [], "lr": lr, "name": name})["params"].append(p)
+    return list(groups.values())
+
+
+def test_fused_adam_matches_reference_golden(built_lib):
+    from s3gaussian_b200.optim import FusedAdam
+    z = np.load(os.path.join(GOLD, "train_adam.npz"))
+    params, grads = mg.adam_inputs(int(z["seed"]), int(z["steps"]))
+    ps = [torch.nn.Parameter(p.clone().to(DEV)) for p in params]
+    opt = FusedAdam(_groups(ps), lr=0.0, eps=1e-15)
+    for s, gs in enumerate(grads):
+        for (name, _, _), p, g in zip(mg.ADAM_SHAPES, ps, gs):
+            p.grad = None if name == "nograd" else g.clone().to(DEV)
+        if s == 2:
+            for gr in opt.param_groups:
+                if gr["name"] == "xyz":
+                    gr["lr"] = 1.0e-4
+        opt.step()
+        for i, p in enumerate(ps):
+            assert rel(p.detach().cpu(), z[f"p{i}_s{s}"]) < 2e-6, (mg.ADAM_SHAPES[i][0], s)
+    for i, p in enumerate(ps):
+        st = opt.state.get(p, {})
+        if mg.ADAM_SHAPES[i][0] == "nograd":
+            assert not st
+            continue
+        assert rel(st["exp_avg"].cpu(), z[f"m{i}"]) < 2e-6 and rel(st["exp_avg_sq"].cpu(), z[f"v{i}"]) < 2e-6
+        assert float(st["step"]) == 3.0
+
+
+def test_fused_adam_matches_torch_adam_many_tensors_and_state_surgery(built_lib):
+    """> 40 tensors (several launches), an unaligned parameter, sizes around the 4096-element chunk, and
+    the reference's optimizer-state surgery (prune + cat, scene/gaussian_model.py:411-470) on the state dict."""
+    from s3gaussian_b200.optim import FusedAdam
+    g = torch.Generator(device=DEV).manual_seed(3)
+    sizes = [1, 3, 4095, 4096, 4097, 8192, 12289, 100003] + [257 + 13 * i for i in range(40)] + [(200000, 3), (200000, 15, 3)]
+    base = []
+    for s in sizes:
+        shape = s if isinstance(s, tuple) else (s,)
+        base.append(torch.randn(*shape, device=DEV, generator=g))
+    storage = torch.randn(5001, device=DEV, generator=g)
+    base.append(storage[1:])                                   # 4-byte offset: not 16-byte aligned
+    ours = [torch.nn.Parameter(b.clone() if b.data_ptr() % 16 == 0 else b) for b in base]
+    ours[-1] = torch.nn.Parameter(storage.clone()[1:])
+    theirs = [torch.nn.Parameter(b.clone()) for b in base]
+    oa = FusedAdam([{"params": [p], "lr": 1e-3 * (1 + i % 3), "name": str(i)} for i, p in enumerate(ours)], lr=0.0, eps=1e-15)
+    ta = torch.optim.Adam([{"params": [p], "lr": 1e-3 * (1 + i % 3), "name": str(i)} for i, p in enumerate(theirs)], lr=0.0, eps=1e-15)
+    for step in range(4):
+        for po, pt in zip(ours, theirs):
+            gr = torch.randn(po.shape, device=DEV, generator=g) * 0.01
+            po.grad, pt.grad = gr.clone(), gr.clone()
+        oa.step(); ta.step()
+    for i, (po, pt) in enumerate(zip(ours, theirs)):
+        assert rel(po, pt) < 2e-6, i
+        assert rel(oa.state[po]["exp_avg"], ta.state[pt]["exp_avg"]) < 2e-6
+        assert rel(oa.state[po]["exp_avg_sq"], ta.state[pt]["exp_avg_sq"]) < 2e-6
+    # prune every other row of the [200000,3] tensor and append 100 rows, on both optimizers, then step again
+    def surgery(opt, plist, idx):
+        group = opt.param_groups[idx]
+        p = group["params"][0]
+        st = opt.state.get(p)
+        mask = torch.arange(p.shape[0], device=DEV) % 2 == 0
+        ext = torch.ones(100, 3, device=DEV)
+        st["exp_avg"] = torch.cat((st["exp_avg"][mask], torch.zeros_like(ext)))
+        st["exp_avg_sq"] = torch.cat((st["exp_avg_sq"][mask], torch.zeros_like(ext)))
+        del opt.state[p]
+        newp = torch.nn.Parameter(torch.cat((p[mask], ext)).requires_grad_(True))
+        group["params"][0] = newp
+        opt.state[newp] = st
+        plist[idx] = newp
+    k = len(sizes) - 2
+    surgery(oa, ours, k); surgery(ta, theirs, k)
+    gr = torch.randn(ours[k].shape, device=DEV, generator=g)
+    for plist in (ours, theirs):
+        for p in plist:
+            p.grad = None
+    ours[k].grad, theirs[k].grad = gr.clone(), gr.clone()
+    oa.step(); ta.step()
+    assert rel(ours[k], theirs[k]) < 2e-6
+    sd = oa.state_dict()
+    assert set(sd["state"][k].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_densify_stats_matches_reference_golden(built_lib):
+    from s3gaussian_b200.optim import add_densification_stats
+    z = np.load(os.path.join(GOLD, "train_densify_stats.npz"))
+    radii, vgrad, accum, denom, max_radii = [t.to(DEV) for t in mg.stats_inputs(int(z["P"]), int(z["seed"]))]
+    add_densification_stats(vgrad, radii, accum, denom, max_radii)
+    assert rel(accum.cpu(), z["accum"]) < 1e-6
+    assert np.array_equal(denom.cpu().numpy(), z["denom"])
+    assert np.array_equal(max_radii.cpu().numpy(), z["max_radii2D"])
+
+
+def test_image_loss_matches_reference_functions_on_gpu(built_lib):
+    """Where oracle/_ref travels: the reference's own l1_loss / ssim / compute_depth (cuDNN depthwise convs)
+    on the same GPU, composed as train.py:395-419."""
+    import ref_ext
+    if not ref_ext.loss_utils_available():
+        pytest.skip("oracle/_ref/s3g_ref/utils/loss_utils.py not present (run oracle/build_ref.sh)")
+    lu = ref_ext.load_ref_loss_utils()
+    from s3gaussian_b200 import losses
+    img, gt, depth, gt_depth = [t.to(DEV) for t in mg.loss_inputs(2, 3, 640, 960, 9)]
+    x = img.clone().requires_grad_(True)
+    d = depth.clone().requires_grad_(True)
+    ours = losses.training_loss(x, gt, d, gt_depth)
+    ours.backward()
+    xr = img.clone().requires_grad_(True)
+    dr = depth.clone().requires_grad_(True)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = lu.l1_loss(xr, gt) + 0.5 * lu.compute_depth("l2", dr, gt_depth) + 0.2 * (1.0 - lu.ssim(xr, gt))
+        ref.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert abs(ours.item() - ref.item()) < 1e-5
+    assert rel(x.grad, xr.grad) < 1e-4
+    assert rel(d.grad, dr.grad) < 1e-5

@@ -1,0 +1,111 @@
+"""Timing of the training-step kernels next to what the reference runs (GPU box).
+  python tools/dev_train.py [--points 2000000] [--width 1920 --height 1280]"""
+import argparse, os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from s3gaussian_b200 import losses, optim
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--points", type=int, default=2000000)
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1280)
+ap.add_argument("--iters", type=int, default=10)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, iters=a.iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+out = {}
+# ---- Adam: the reference's eight groups at P Gaussians + the HexPlane/MLP parameters --------
+P = a.points
+shapes = [("xyz", (P, 3)), ("f_dc", (P, 1, 3)), ("f_rest", (P, 15, 3)), ("opacity", (P, 1)), ("scaling", (P, 3)), ("rotation", (P, 4))]
+reso, mult = [64, 64, 64, 25], [1, 2, 4, 8]
+import itertools
+for m in mult:
+    r = [reso[0] * m, reso[1] * m, reso[2] * m, reso[3]]
+    for ca, cb in itertools.combinations(range(4), 2):
+        shapes.append(("grid", (1, 32, r[cb], r[ca])))
+for _ in range(14):
+    shapes.append(("deformation", (64, 64)))
+shapes.append(("deformation", (64, 128)))
+nel = sum(int(torch.tensor(s).prod()) for _, s in shapes)
+
+
+def make(opt_cls):
+    ps = [torch.nn.Parameter(torch.randn(*s, device=dev) * 0.1) for _, s in shapes]
+    groups = {}
+    for (n, _), p in zip(shapes, ps):
+        groups.setdefault(n, {"params": [], "lr": 1e-3, "name": n})["params"].append(p)
+    opt = opt_cls(list(groups.values()), lr=0.0, eps=1e-15)
+    for p in ps:
+        p.grad = torch.randn_like(p) * 0.01
+    return ps, opt
+
+
+ps, opt = make(optim.FusedAdam)
+t_ours = timeit(opt.step)
+del ps, opt
+torch.cuda.empty_cache()
+ps, opt = make(torch.optim.Adam)
+t_ref = timeit(opt.step)
+del ps, opt
+torch.cuda.empty_cache()
+out["adam"] = {"elements": nel, "ours_ms": t_ours, "torch_adam_ms": t_ref, "ours_GBps": nel * 28 / t_ours / 1e6,
+               "speedup": t_ref / t_ours}
+
+# ---- image loss fwd+bwd ---------------------------------------------------------------------
+H, W = a.height, a.width
+g = torch.Generator(device=dev).manual_seed(0)
+gt = torch.rand(1, 3, H, W, device=dev, generator=g)
+img = (gt + 0.1 * torch.randn(1, 3, H, W, device=dev, generator=g)).clamp(0, 1)
+gtd = torch.rand(1, 1, H, W, device=dev, generator=g) * 100
+dep = (gtd + torch.randn(1, 1, H, W, device=dev, generator=g)).abs()
+
+
+def ours_loss():
+    x = img.clone().requires_grad_(True); d = dep.clone().requires_grad_(True)
+    losses.training_loss(x, gt, d, gtd).backward()
+
+
+t_ours = timeit(ours_loss)
+res = {"ours_ms": t_ours}
+import ref_ext
+if ref_ext.loss_utils_available():
+    lu = ref_ext.load_ref_loss_utils()
+
+    def ref_loss():
+        x = img.clone().requires_grad_(True); d = dep.clone().requires_grad_(True)
+        (lu.l1_loss(x, gt) + 0.5 * lu.compute_depth("l2", d, gtd) + 0.2 * (1.0 - lu.ssim(x, gt))).backward()
+    res["reference_ms"] = timeit(ref_loss)
+    res["speedup"] = res["reference_ms"] / t_ours
+out["image_loss"] = res
+
+# ---- densify stats ------------------------------------------------------------------------------
+radii = torch.randint(0, 30, (P,), device=dev, dtype=torch.int32)
+vg = torch.randn(P, 3, device=dev)
+acc, den, mr = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, device=dev)
+t_ours = timeit(lambda: optim.add_densification_stats(vg, radii, acc, den, mr))
+
+
+def ref_stats():
+    vis = radii > 0
+    mr[vis] = torch.max(mr[vis], radii[vis])
+    acc[vis] += torch.norm(vg[vis, :2], dim=-1, keepdim=True)
+    den[vis] += 1
+
+
+out["densify_stats"] = {"ours_ms": t_ours, "torch_ms": timeit(ref_stats)}
+print(json.dumps(out))

@@ -57,6 +57,8 @@ def parse():
                          "HexPlane + decoder + rgb/depth pass + feat pass, fwd+bwd (BASELINE config 3 shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--no-train-iteration", action="store_true",
+                    help="skip the whole-training-iteration leg (render + loss + stats + Adam, N == 1 only)")
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     return ap.parse_args()
 
@@ -100,6 +102,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+ref_ext_mod = None
+
+
 def load_impl(name):
     if name == "ours":
         from s3gaussian_b200 import build
@@ -107,6 +112,8 @@ def load_impl(name):
         from s3gaussian_b200 import diff_gaussian_rasterization as m
         return m
     import ref_ext
+    global ref_ext_mod
+    ref_ext_mod = ref_ext
     if not ref_ext.available():
         return None
     return ref_ext.load()
@@ -281,6 +288,61 @@ def main():
                "sample": f"first {n} Gaussians of the workload cloud, same camera and resolution, fwd+bwd, "
                          f"oracle/splat_oracle.c single thread, {dt:.1f} s; host has {os.cpu_count()} cores"}
 
+    # ---- whole training iteration (N == 1): render + image loss + backward + densify stats + Adam ----
+    # SURVEY 8f rows f-1/f-2 either side of the rasterizer.  Ours: fused loss / stats / Adam kernels; reference
+    # arm: the reference's own loss_utils + torch.optim.Adam(eps=1e-15) + the torch statements of train.py:489-491.
+    # Runs last because Adam moves the parameters (learning rates are tiny: this is a timing leg).
+    train_it = None
+    if world == 1 and not a.no_train_iteration:
+        params = [v for v in leaves if v is not m2d]
+        groups = [{"params": [v], "lr": 1e-6, "name": str(i)} for i, v in enumerate(params)]
+        acc = torch.zeros(P, 1, device=dev)
+        den = torch.zeros(P, 1, device=dev)
+        maxr = torch.zeros(P, device=dev)
+        img_d, dep_d = gt_img.to(dev), gt_dep.to(dev)
+        if a.impl == "ours":
+            from s3gaussian_b200 import losses, optim
+            opt = optim.FusedAdam(groups, lr=0.0, eps=1e-15)
+
+            def loss_fn(color, depth):
+                return losses.training_loss(color, img_d, depth, dep_d)
+
+            def stats_fn(radii):
+                optim.add_densification_stats(m2d.grad, radii, acc, den, maxr)
+            what = "render fwd+bwd, fused L1+SSIM+depth loss, fused densify stats, FusedAdam step (5 launches + rasterizer)"
+        else:
+            opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+            lu = None
+            if ref_ext_mod.loss_utils_available():
+                lu = ref_ext_mod.load_ref_loss_utils()
+
+            def loss_fn(color, depth):
+                if lu is None:
+                    return (color - img_d).abs().mean() + 0.5 * ((depth - dep_d) ** 2).mean()
+                return lu.l1_loss(color, img_d) + 0.5 * lu.compute_depth("l2", depth, dep_d) + \
+                    0.2 * (1.0 - lu.ssim(color.unsqueeze(0), img_d.unsqueeze(0)))
+
+            def stats_fn(radii):
+                vis = radii > 0
+                maxr[vis] = torch.max(maxr[vis], radii[vis])
+                acc[vis] += torch.norm(m2d.grad[vis, :2], dim=-1, keepdim=True)
+                den[vis] += 1
+            what = ("reference extension fwd+bwd, reference utils/loss_utils.py (l1 + ssim + depth l2), torch statements of "
+                    "train.py:489-491, torch.optim.Adam(eps=1e-15).step()") if lu is not None else \
+                   "reference extension + plain L1/L2 loss (loss_utils.py not in oracle/_ref) + torch Adam"
+
+        def step_train():
+            zero_grads()
+            color, radii, depth = rast(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"],
+                                       colors_precomp=t["colors_precomp"], scales=t["scales"],
+                                       rotations=t["rotations"], cov3D_precomp=None)
+            loss_fn(color, depth).backward()
+            with torch.no_grad():
+                stats_fn(radii)
+            opt.step()
+        ms_train = timed(step_train, 10, 3)
+        train_it = {"ms": round(ms_train / 10, 4), "iterations": 10, "what": what}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,6 +380,8 @@ def main():
         out["stages"] = stages
         if cpu:
             out["cpu_baseline"] = cpu
+    if train_it:
+        out["train_iteration"] = train_it
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

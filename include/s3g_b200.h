@@ -296,6 +296,25 @@ int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, cons
                             const float* weights, const double* sums, const void* workspace,
                             float* g_image, float* g_depth, void* stream);
 
+/* ---- HexPlane regularisers -------------------------------------------
+ * s3g_plane_reg_*  <- GaussianModel.compute_regulation                 scene/gaussian_model.py:710-749
+ *                     + compute_plane_smoothness                        scene/regulation.py:22-28
+ * total = sum_planes  w_smooth * mean((t[h+2]-2t[h+1]+t[h])^2 over [1,C,H-2,W]) + w_l1 * mean|1-t|
+ * Each plane is the [1,C,H,W] tensor stored channels-last, i.e. physically [H][W][C]; C % 4 == 0, H >= 3.
+ * `planes` is a HOST array (device pointers inside), n <= 48.  forward: total = DEVICE double[1],
+ * workspace of s3g_plane_reg_workspace_bytes(...) bytes.  backward: gscale = DEVICE float[1] (the
+ * upstream gradient); OVERWRITES planes[i].grad (same physical layout) with gscale * d total/d plane. */
+typedef struct s3g_plane_desc {
+    const float* plane;
+    float* grad;          /* backward only */
+    int H, W, C;
+    float w_smooth;
+    float w_l1;
+} s3g_plane_desc;
+size_t s3g_plane_reg_workspace_bytes(int n, const s3g_plane_desc* planes);
+int s3g_plane_reg_forward(int n, const s3g_plane_desc* planes, double* total, void* workspace, void* stream);
+int s3g_plane_reg_backward(int n, const s3g_plane_desc* planes, const float* gscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

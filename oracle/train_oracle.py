@@ -5,6 +5,8 @@ Restates (paths relative to /root/reference):
   l1_loss, gaussian/create_window/_ssim, compute_depth("l2")   utils/loss_utils.py:20-96
   loss composition                                             train.py:395-419
   max_radii2D update + add_densification_stats                 train.py:489-491, scene/gaussian_model.py:693-695
+  compute_plane_smoothness, _plane/_time/_l1_regulation,       scene/regulation.py:22-28,
+  compute_regulation                                           scene/gaussian_model.py:710-749
 Third-party arithmetic restated from its documented behaviour: torch.optim.Adam (call site
 scene/gaussian_model.py:189 `torch.optim.Adam(l, lr=0.0, eps=1e-15)`, amsgrad off, no weight decay):
     m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
@@ -94,3 +96,25 @@ def densify_stats(viewspace_grad, radii, accum, denom, max_radii2D):
     accum[vis] = accum[vis] + viewspace_grad[vis, :2].norm(dim=-1, keepdim=True).reshape(accum[vis].shape)
     denom[vis] = denom[vis] + 1
     return accum, denom, max_radii2D
+
+
+def plane_smoothness(t):
+    """scene/regulation.py:22-28: mean squared second difference along dim 2 of [B,C,H,W]."""
+    h = t.shape[2]
+    first = t[..., 1:, :] - t[..., :h - 1, :]
+    second = first[..., 1:, :] - first[..., :h - 2, :]
+    return (second ** 2).mean()
+
+
+def compute_regulation(multi_res_grids, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight):
+    """scene/gaussian_model.py:710-749: planes 0,1,3 spatial, 2,4,5 spatio-temporal; 3-plane levels skipped."""
+    plane_reg = time_reg = l1_reg = 0.0
+    for grids in multi_res_grids:
+        if len(grids) == 3:
+            continue
+        for k in (0, 1, 3):
+            plane_reg = plane_reg + plane_smoothness(grids[k])
+        for k in (2, 4, 5):
+            time_reg = time_reg + plane_smoothness(grids[k])
+            l1_reg = l1_reg + (1 - grids[k]).abs().mean()
+    return plane_tv_weight * plane_reg + time_smoothness_weight * time_reg + l1_time_planes_weight * l1_reg

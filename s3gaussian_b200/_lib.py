@@ -52,6 +52,9 @@ SIGNATURES = {
     "s3g_densify_stats": (_I, [_I, _V, _V, _V, _V, _V, _V]),
     "s3g_image_loss_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "s3g_image_loss_forward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V]),
+    "s3g_plane_reg_workspace_bytes": (_SZ, [_I, _V]),
+    "s3g_plane_reg_forward": (_I, [_I, _V, _V, _V, _V]),
+    "s3g_plane_reg_backward": (_I, [_I, _V, _V, _V]),
     "s3g_image_loss_backward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V, _V, _V]),
 }
 
@@ -110,3 +113,9 @@ def profile_read(which: int) -> dict:
     buf = (C.c_float * 16)()
     n = check(lib.s3g_profile_read(which, buf, 16), "s3g_profile_read")
     return {lib.s3g_profile_stage_name(which, i).decode(): float(buf[i]) for i in range(n)}
+
+
+class PlaneDesc(C.Structure):
+    """s3g_plane_desc (include/s3g_b200.h)."""
+    _fields_ = [("plane", C.c_void_p), ("grad", C.c_void_p), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+                ("w_smooth", C.c_float), ("w_l1", C.c_float)]

@@ -869,4 +869,60 @@ int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, cons
     return S3G_OK;
 }
 
+// ---- HexPlane regularisers -------------------------------------------------------------------
+namespace {
+int reg_table(int n, const s3g_plane_desc* planes, bool need_grad, RegArgs& a) {
+    if (n <= 0 || n > REG_MAX_PLANES || !planes) return fail(S3G_ERR_ARG, "plane_reg: 1..48 planes expected");
+    int blocks = 0;
+    a.count = n;
+    for (int i = 0; i < n; ++i) {
+        const s3g_plane_desc& d = planes[i];
+        if (!d.plane || (need_grad && !d.grad)) return fail(S3G_ERR_ARG, "plane_reg: null plane / grad pointer");
+        if (d.H < 3 || d.W < 1 || d.C < 4 || d.C % 4) return fail(S3G_ERR_ARG, "plane_reg: need H >= 3, W >= 1, C % 4 == 0");
+        RegPlane& p = a.p[i];
+        p.t = d.plane; p.g = d.grad; p.H = d.H; p.W = d.W; p.C = d.C;
+        p.k_smooth = (float)((double)d.w_smooth / ((double)d.C * (d.H - 2) * d.W));
+        p.k_l1 = (float)((double)d.w_l1 / ((double)d.C * d.H * d.W));
+        const long long n4 = (long long)d.H * d.W * d.C / 4;
+        a.block_start[i] = blocks;
+        const long long nb = (n4 + REG_CHUNK4 - 1) / REG_CHUNK4;
+        if (blocks + nb > 0x7fffffffLL) return fail(S3G_ERR_ARG, "plane_reg: planes too large");
+        blocks += (int)nb;
+    }
+    a.block_start[n] = blocks;
+    return blocks;
+}
+}  // namespace
+
+size_t s3g_plane_reg_workspace_bytes(int n, const s3g_plane_desc* planes) {
+    RegArgs a;
+    const int blocks = reg_table(n, planes, false, a);
+    return blocks < 0 ? 0 : 256 + sizeof(double) * (size_t)blocks;
+}
+
+int s3g_plane_reg_forward(int n, const s3g_plane_desc* planes, double* total, void* workspace, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RegArgs a;
+    const int blocks = reg_table(n, planes, false, a);
+    if (blocks < 0) return blocks;
+    if (!total || !workspace) return fail(S3G_ERR_ARG, "plane_reg_forward: null total/workspace");
+    double* partial = reinterpret_cast<double*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    plane_reg_forward_kernel<<<blocks, REG_THREADS, 0, stream>>>(a, partial);
+    S3G_CUDA(cudaGetLastError(), "plane_reg_forward launch");
+    plane_reg_reduce_kernel<<<1, 256, 0, stream>>>(blocks, partial, total);
+    S3G_CUDA(cudaGetLastError(), "plane_reg_reduce launch");
+    return S3G_OK;
+}
+
+int s3g_plane_reg_backward(int n, const s3g_plane_desc* planes, const float* gscale, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RegArgs a;
+    const int blocks = reg_table(n, planes, true, a);
+    if (blocks < 0) return blocks;
+    if (!gscale) return fail(S3G_ERR_ARG, "plane_reg_backward: null gscale");
+    plane_reg_backward_kernel<<<blocks, REG_THREADS, 0, stream>>>(a, gscale);
+    S3G_CUDA(cudaGetLastError(), "plane_reg_backward launch");
+    return S3G_OK;
+}
+
 }  // extern "C"

@@ -332,4 +332,132 @@ __global__ void __launch_bounds__(256) loss_depth_grad_kernel(size_t n, const fl
     g_out[i] = r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HexPlane regularisers (GaussianModel.compute_regulation, scene/gaussian_model.py:710-749 with
+// compute_plane_smoothness of scene/regulation.py:22-28):
+//   total = sum over planes of  w_smooth * mean((t[h+2] - 2 t[h+1] + t[h])^2)  +  w_l1 * mean|1 - t|
+// (second difference along dim 2 of the [1,C,H,W] tensor; w_smooth = plane_tv_weight on the spatial
+// planes 0,1,3 and time_smoothness_weight on the time planes 2,4,5, which also carry the L1 term).
+// Planes live channels-last ([H][W][C], the layout the sampling kernels use), so a step along H is a
+// stride of W*C floats and every access below is a coalesced float4.  Forward = one read pass with
+// per-block partial sums; backward = one read pass (5-tap stencil of the fourth difference) + one write.
+// ---------------------------------------------------------------------------------------------
+constexpr int REG_THREADS = 256;
+constexpr int REG_VEC = 4;
+constexpr int REG_CHUNK4 = REG_THREADS * REG_VEC;      // float4 elements per block
+constexpr int REG_MAX_PLANES = 48;
+
+struct RegPlane {
+    const float* t;
+    float* g;
+    int H, W, C;
+    float k_smooth;     // w_smooth / (C (H-2) W)
+    float k_l1;         // w_l1 / (C H W)
+};
+struct RegArgs {
+    RegPlane p[REG_MAX_PLANES];
+    int block_start[REG_MAX_PLANES + 1];
+    int count;
+};
+
+__device__ __forceinline__ int reg_find(const RegArgs& a, int b) {
+    int lo = 0, hi = a.count;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.block_start[mid] <= b) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 sd4(float4 a, float4 b, float4 c) {   // a - 2b + c
+    return make_float4(a.x - 2.f * b.x + c.x, a.y - 2.f * b.y + c.y, a.z - 2.f * b.z + c.z, a.w - 2.f * b.w + c.w);
+}
+
+__global__ void __launch_bounds__(REG_THREADS) plane_reg_forward_kernel(const __grid_constant__ RegArgs a,
+                                                                       double* __restrict__ partial) {
+    __shared__ double red[REG_THREADS / 32];
+    const int pi = reg_find(a, blockIdx.x);
+    const RegPlane& pl = a.p[pi];
+    const long long row4 = (long long)pl.W * pl.C / 4;          // float4 per H step
+    const long long n4 = row4 * pl.H;
+    const long long base = (long long)(blockIdx.x - a.block_start[pi]) * REG_CHUNK4;
+    float s_sm = 0.f, s_l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < REG_VEC; ++j) {
+        const long long i = base + j * REG_THREADS + threadIdx.x;
+        if (i >= n4) continue;
+        const int h = (int)(i / row4);
+        const float4 t0 = ld4(pl.t + 4 * i);
+        if (pl.k_l1 != 0.f) s_l1 += fabsf(1.f - t0.x) + fabsf(1.f - t0.y) + fabsf(1.f - t0.z) + fabsf(1.f - t0.w);
+        if (h + 2 < pl.H) {
+            const float4 d = sd4(t0, ld4(pl.t + 4 * (i + row4)), ld4(pl.t + 4 * (i + 2 * row4)));
+            s_sm += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        }
+    }
+    double v = (double)s_sm * (double)pl.k_smooth + (double)s_l1 * (double)pl.k_l1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < REG_THREADS / 32; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) plane_reg_reduce_kernel(int n, const double* __restrict__ partial,
+                                                              double* __restrict__ total) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = red[0];
+}
+
+// grad[h] = gscale * ( 2 k_smooth (d[h-2] - 2 d[h-1] + d[h]) - k_l1 sign(1 - t[h]) ),  d[j] = t[j] - 2 t[j+1] + t[j+2]
+// for 0 <= j <= H-3 and 0 elsewhere.
+__global__ void __launch_bounds__(REG_THREADS) plane_reg_backward_kernel(const __grid_constant__ RegArgs a,
+                                                                        const float* __restrict__ gscale) {
+    const int pi = reg_find(a, blockIdx.x);
+    const RegPlane& pl = a.p[pi];
+    const long long row4 = (long long)pl.W * pl.C / 4;
+    const long long n4 = row4 * pl.H;
+    const long long base = (long long)(blockIdx.x - a.block_start[pi]) * REG_CHUNK4;
+    const float gs = __ldg(gscale);
+    const float ks = 2.f * pl.k_smooth * gs, kl = pl.k_l1 * gs;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < REG_VEC; ++j) {
+        const long long i = base + j * REG_THREADS + threadIdx.x;
+        if (i >= n4) continue;
+        const int h = (int)(i / row4);
+        const int H = pl.H;
+        const float* c = pl.t + 4 * i;
+        const float4 t0 = ld4(c);
+        const float4 tm2 = h >= 2 ? ld4(c - 8 * row4) : z, tm1 = h >= 1 ? ld4(c - 4 * row4) : z;
+        const float4 tp1 = h + 1 < H ? ld4(c + 4 * row4) : z, tp2 = h + 2 < H ? ld4(c + 8 * row4) : z;
+        // d[h-2] exists if h-2 >= 0 (and h <= H-1 always holds for its last tap); d[h-1] if h-1 >= 0 and h+1 <= H-1;
+        // d[h] if h+2 <= H-1
+        const float4 dm2 = h >= 2 ? sd4(tm2, tm1, t0) : z;
+        const float4 dm1 = (h >= 1 && h + 1 < H) ? sd4(tm1, t0, tp1) : z;
+        const float4 d0 = (h + 2 < H) ? sd4(t0, tp1, tp2) : z;
+        float4 g = sd4(dm2, dm1, d0);
+        g.x *= ks; g.y *= ks; g.z *= ks; g.w *= ks;
+        if (kl != 0.f) {
+            g.x -= kl * (t0.x < 1.f ? 1.f : (t0.x > 1.f ? -1.f : 0.f));
+            g.y -= kl * (t0.y < 1.f ? 1.f : (t0.y > 1.f ? -1.f : 0.f));
+            g.z -= kl * (t0.z < 1.f ? 1.f : (t0.z > 1.f ? -1.f : 0.f));
+            g.w -= kl * (t0.w < 1.f ? 1.f : (t0.w > 1.f ? -1.f : 0.f));
+        }
+        *reinterpret_cast<float4*>(pl.g + 4 * i) = g;
+    }
+}
+
 }  // namespace s3g

@@ -51,6 +51,12 @@ class GaussianModelLite(nn.Module):
     def _deformation_table(self):
         return torch.ones(self._xyz.shape[0], dtype=torch.bool, device=self._xyz.device)
 
+    def compute_regulation(self, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight):
+        """scene/gaussian_model.py:748-749, one fused launch per direction (regulation.py)."""
+        from .regulation import compute_regulation
+        return compute_regulation(self._deformation.deformation_net.grid.grids, time_smoothness_weight,
+                                  l1_time_planes_weight, plane_tv_weight)
+
     def get_covariance(self, scaling_modifier=1):
         s = scaling_modifier * torch.exp(self._scaling)
         q = torch.nn.functional.normalize(self._rotation)

@@ -61,14 +61,20 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad
                 if g.is_sparse:
                     raise RuntimeError("FusedAdam does not support sparse gradients")
-                if not p.is_contiguous():
-                    raise RuntimeError("FusedAdam: parameters must be contiguous")
-                if not g.is_contiguous():
-                    g = g.contiguous()
+                # the update is elementwise: any dense layout works as long as all four tensors share it
+                # (HexPlane planes are channels_last)
+                if p.is_contiguous():
+                    fmt = torch.contiguous_format
+                elif p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last):
+                    fmt = torch.channels_last
+                else:
+                    raise RuntimeError("FusedAdam: parameters must be dense (contiguous or channels_last)")
+                if g.stride() != p.stride():
+                    g = g.contiguous(memory_format=fmt)
                 st = self._init_state(p)
-                if not (st["exp_avg"].is_contiguous() and st["exp_avg_sq"].is_contiguous()):
-                    st["exp_avg"] = st["exp_avg"].contiguous()
-                    st["exp_avg_sq"] = st["exp_avg_sq"].contiguous()
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if st[k].stride() != p.stride():
+                        st[k] = st[k].contiguous(memory_format=fmt)
                 st["step"] += 1
                 keep.append(g)
                 by_key.setdefault((p.device.index, float(b1), float(b2), float(group["eps"])), []).append(

@@ -183,3 +183,54 @@ def test_image_loss_matches_reference_functions_on_gpu(built_lib):
     assert abs(ours.item() - ref.item()) < 1e-5
     assert rel(x.grad, xr.grad) < 1e-4
     assert rel(d.grad, dr.grad) < 1e-5
+
+
+def test_plane_regulation_matches_reference_golden(built_lib):
+    from s3gaussian_b200 import regulation
+    z = np.load(os.path.join(GOLD, "train_plane_reg.npz"))
+    levels = [[p.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for p in lv]
+              for lv in mg.reg_inputs(int(z["seed"]))]
+    total = regulation.compute_regulation(levels, 0.01, 0.0001, 0.0001)
+    (3.0 * total).backward()
+    assert abs(total.item() - float(z["total"])) < 2e-6 * abs(float(z["total"]))
+    for l, lv in enumerate(levels):
+        for k, p in enumerate(lv):
+            assert rel(p.grad.cpu(), 3.0 * z[f"g{l}_{k}"]) < 1e-5, (l, k)
+    one = levels[0][2]
+    from oracle import train_oracle as tro
+    assert abs(regulation.compute_plane_smoothness(one).item() - tro.plane_smoothness(one.detach().cpu().double()).item()) < 1e-6
+
+
+def test_plane_regulation_full_size_and_adam_on_channels_last_planes(built_lib):
+    """The shipped HexPlane (4 levels, 142.9 MB): regulariser vs the oracle on the GPU, then one FusedAdam step
+    on the channels_last planes vs torch.optim.Adam."""
+    from oracle import train_oracle as tro
+    from s3gaussian_b200 import regulation, synthetic as syn
+    from s3gaussian_b200.deformation import deform_network
+    from s3gaussian_b200.optim import FusedAdam
+    import ref_ext
+    net = deform_network(ref_ext.ref_deform_args(syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES)).to(DEV)
+    grids = net.deformation_net.grid.grids
+    g = torch.Generator(device=DEV).manual_seed(1)
+    with torch.no_grad():
+        for lv in grids:
+            for p in lv:
+                p.add_(0.05 * torch.randn(p.shape, device=DEV, generator=g).contiguous(memory_format=torch.channels_last))
+    total = regulation.compute_regulation(grids, 0.01, 0.0001, 0.0001)
+    total.backward()
+    ref_planes = [[p.detach().double().requires_grad_(True) for p in lv] for lv in grids]
+    ref = tro.compute_regulation(ref_planes, 0.01, 0.0001, 0.0001)
+    ref.backward()
+    assert abs(total.item() - ref.item()) < 1e-5 * abs(ref.item())
+    for lv, rlv in zip(grids, ref_planes):
+        for p, r in zip(lv, rlv):
+            assert p.grad.stride() == p.stride()
+            assert rel(p.grad, r.grad) < 1e-5
+    planes = [p for lv in grids for p in lv]
+    clones = [torch.nn.Parameter(p.detach().clone()) for p in planes]
+    for c, p in zip(clones, planes):
+        c.grad = p.grad.clone()
+    FusedAdam([{"params": planes, "lr": 1.6e-3, "name": "grid"}], lr=0.0, eps=1e-15).step()
+    torch.optim.Adam([{"params": clones, "lr": 1.6e-3, "name": "grid"}], lr=0.0, eps=1e-15).step()
+    for c, p in zip(clones, planes):
+        assert rel(p, c) < 2e-6

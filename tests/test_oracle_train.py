@@ -77,3 +77,14 @@ def test_densify_stats_oracle_matches_reference():
     assert rel(a, z["accum"]) < 1e-6
     assert np.array_equal(d.numpy(), z["denom"])
     assert np.array_equal(m.numpy(), z["max_radii2D"])
+
+
+def test_plane_regulation_oracle_matches_reference():
+    z = np.load(os.path.join(GOLD, "train_plane_reg.npz"))
+    levels = [[p.double().requires_grad_(True) for p in lv] for lv in mg.reg_inputs(int(z["seed"]))]
+    total = tro.compute_regulation(levels, 0.01, 0.0001, 0.0001)
+    total.backward()
+    assert abs(total.item() - float(z["total"])) < 1e-6 * abs(float(z["total"]))
+    for l, lv in enumerate(levels):
+        for k, p in enumerate(lv):
+            assert rel(p.grad, z[f"g{l}_{k}"]) < 1e-5, (l, k)

@@ -108,4 +108,28 @@ def ref_stats():
 
 
 out["densify_stats"] = {"ours_ms": t_ours, "torch_ms": timeit(ref_stats)}
+# ---- plane regularisers on the shipped HexPlane ----------------------------------------------
+from s3gaussian_b200 import regulation, synthetic as syn
+from s3gaussian_b200.deformation import deform_network
+from oracle import train_oracle as tro
+import ref_ext as _re
+net = deform_network(_re.ref_deform_args(syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES)).to(dev)
+grids = net.deformation_net.grid.grids
+
+
+def ours_reg():
+    for lv in grids:
+        for p in lv:
+            p.grad = None
+    regulation.compute_regulation(grids, 0.01, 0.0001, 0.0001).backward()
+
+
+def torch_reg():     # the same torch statements the reference runs (oracle restatement, fp32, on the GPU)
+    for lv in grids:
+        for p in lv:
+            p.grad = None
+    tro.compute_regulation(grids, 0.01, 0.0001, 0.0001).backward()
+
+
+out["plane_regulation"] = {"ours_ms": timeit(ours_reg), "torch_ms": timeit(torch_reg)}
 print(json.dumps(out))

@@ -4,6 +4,8 @@
                composed as train.py:395-419 does, gradients from autograd.
   adam case  : the optimizer the reference constructs (scene/gaussian_model.py:176-189): torch.optim.Adam
                with its eight named groups, lr=0.0 default, eps=1e-15, stepped three times.
+  reg case   : GaussianModel.compute_regulation + its three helpers (scene/gaussian_model.py:710-749) and
+               compute_plane_smoothness (scene/regulation.py:22-28), all extracted with ast and run as they are.
   stats case : the two statements of train.py:489-491 executed verbatim around the reference's own
                GaussianModel.add_densification_stats, whose source is extracted from
                scene/gaussian_model.py with ast (the module itself needs simple_knn/open3d to import).
@@ -105,15 +107,47 @@ def make_adam(outdir):
     print("adam ok")
 
 
-def reference_method(name):
-    src = open(f"{REF}/scene/gaussian_model.py").read()
+def reference_method(name, file="scene/gaussian_model.py", ns=None):
+    src = open(f"{REF}/{file}").read()
     for node in ast.walk(ast.parse(src)):
         if isinstance(node, ast.FunctionDef) and node.name == name:
             mod = ast.Module(body=[node], type_ignores=[])
-            ns = {"torch": torch}
-            exec(compile(mod, f"{REF}/scene/gaussian_model.py", "exec"), ns)
+            ns = {"torch": torch} if ns is None else ns
+            exec(compile(mod, f"{REF}/{file}", "exec"), ns)
             return ns[name]
     raise KeyError(name)
+
+
+def reg_inputs(seed=41, resolution=(8, 6, 5, 7), multires=(1, 2), channels=32):
+    """planes shaped like init_grid_param (scene/hexplane.py:48-70): [1,C,reso[b],reso[a]] per comb (a,b)."""
+    import itertools
+    g = torch.Generator().manual_seed(seed)
+    levels = []
+    for m in multires:
+        reso = [r * m for r in resolution[:3]] + [resolution[3]]
+        planes = []
+        for ca, cb in itertools.combinations(range(4), 2):
+            t = torch.rand(1, channels, reso[cb], reso[ca], generator=g) * 0.8 + 0.6      # straddles 1 for the L1 sign
+            planes.append(t)
+        levels.append(planes)
+    return levels
+
+
+def make_reg(outdir):
+    ns = {"torch": torch}
+    reference_method("compute_plane_smoothness", "scene/regulation.py", ns)
+    for m in ("_plane_regulation", "_time_regulation", "_l1_regulation", "compute_regulation"):
+        reference_method(m, ns=ns)
+    levels = [[p.clone().requires_grad_(True) for p in lv] for lv in reg_inputs()]
+    model = types.SimpleNamespace()
+    model._deformation = types.SimpleNamespace(deformation_net=types.SimpleNamespace(grid=types.SimpleNamespace(grids=levels)))
+    for m in ("_plane_regulation", "_time_regulation", "_l1_regulation"):
+        setattr(model, m, types.MethodType(ns[m], model))
+    total = ns["compute_regulation"](model, 0.01, 0.0001, 0.0001)       # arguments/__init__.py:213-215 defaults
+    total.backward()
+    out = {f"g{l}_{k}": p.grad.numpy() for l, lv in enumerate(levels) for k, p in enumerate(lv)}
+    np.savez_compressed(os.path.join(outdir, "train_plane_reg.npz"), seed=41, total=total.item(), **out)
+    print("reg", total.item())
 
 
 def stats_inputs(P=5000, seed=31):
@@ -147,3 +181,4 @@ if __name__ == "__main__":
     make_loss(out, import_loss_utils())
     make_adam(out)
     make_stats(out)
+    make_reg(out)

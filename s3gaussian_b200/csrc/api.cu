@@ -713,7 +713,8 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int blocks = std::min((P + 7) / 8, sms * 8);
-        hexplane_scatter_kernel<<<blocks, 256, 0, stream>>>(sc);
+        if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
+        else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
         S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
     }
     {

@@ -50,7 +50,17 @@ __host__ __device__ constexpr int comb_a(int k) { return k < 3 ? 0 : (k < 5 ? 1 
 __host__ __device__ constexpr int comb_b(int k) { return k == 0 ? 1 : (k == 1 ? 2 : (k == 2 ? 3 : (k == 3 ? 2 : 3))); }
 
 // ---- 3xTF32 tensor-core tile product ----------------------------------------
+// x = hi + lo with hi, lo representable in tf32.  The tensor cores read sign, exponent and the top 10
+// mantissa bits of a tf32 operand and ignore the rest (truncation), so hi is x itself and lo the exact
+// remainder x - trunc(x), passed as is (its own truncation error is <= 2^-20 |x|).  Two instructions;
+// cvt.rna.tf32.f32 is emulated on sm_100a with four ALU instructions per conversion (FSETP/IADD3/SEL/LOP3),
+// and the rounding split was 40 % of the backward decoder's instruction stream (profiles/r01e).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+// round-to-nearest variant for data that is split once and reused (weights of the tcgen05 path)
+__device__ __forceinline__ void split_tf32_rna(float x, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     const float r = x - __uint_as_float(hi);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
@@ -540,30 +550,41 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
                                          float* __restrict__ gW, float* __restrict__ gb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     constexpr int TN = NIN / 8;
-    constexpr int TILES = (M / 16) * TN;
-    for (int tile = warp; tile < TILES; tile += DTHREADS / 32) {
-        const int m0 = (tile / TN) * 16, n0 = (tile % TN) * 8;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int NT = 4;                        // n-tiles per work item: the delta fragment is split once for all of them
+    static_assert(TN % NT == 0, "dw_accum: NIN must be a multiple of 32");
+    constexpr int ITEMS = (M / 16) * (TN / NT);
+    for (int item = warp; item < ITEMS; item += DTHREADS / 32) {
+        const int m0 = (item / (TN / NT)) * 16, n0 = (item % (TN / NT)) * (8 * NT);
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 2
         for (int k0 = 0; k0 < DT; k0 += 8) {
             // A[m][k] = delta[k][m]
             const float a[4] = {sDelta[(k0 + t) * dStride + m0 + g], sDelta[(k0 + t) * dStride + m0 + g + 8],
                                 sDelta[(k0 + t + 4) * dStride + m0 + g], sDelta[(k0 + t + 4) * dStride + m0 + g + 8]};
-            float b[2] = {sAct[(k0 + t) * aStride + n0 + g], sAct[(k0 + t + 4) * aStride + n0 + g]};
-            if (RELU_ACT) { b[0] = fmaxf(b[0], 0.f); b[1] = fmaxf(b[1], 0.f); }
-            uint32_t ah[4], al[4], bh[2], bl[2];
+            uint32_t ah[4], al[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
-            split_tf32(b[0], bh[0], bl[0]);
-            split_tf32(b[1], bh[1], bl[1]);
-            mma3(acc, ah, al, bh, bl);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                float b[2] = {sAct[(k0 + t) * aStride + n0 + 8 * j + g], sAct[(k0 + t + 4) * aStride + n0 + 8 * j + g]};
+                if (RELU_ACT) { b[0] = fmaxf(b[0], 0.f); b[1] = fmaxf(b[1], 0.f); }
+                uint32_t bh[2], bl[2];
+                split_tf32(b[0], bh[0], bl[0]);
+                split_tf32(b[1], bh[1], bl[1]);
+                mma3(acc[j], ah, al, bh, bl);
+            }
         }
         // fire-and-forget REDs on the CTA-private partial buffer: a load-add-store would expose
         // one L2 round trip per output tile (measured: 14 ms of a 55 ms step)
-        float* p0 = gW + (size_t)(m0 + g) * NIN + n0 + 2 * t;
-        float* p1 = gW + (size_t)(m0 + g + 8) * NIN + n0 + 2 * t;
-        atomicAdd(p0, acc[0]); atomicAdd(p0 + 1, acc[1]);
-        atomicAdd(p1, acc[2]); atomicAdd(p1 + 1, acc[3]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            float* p0 = gW + (size_t)(m0 + g) * NIN + n0 + 8 * j + 2 * t;
+            float* p1 = gW + (size_t)(m0 + g + 8) * NIN + n0 + 8 * j + 2 * t;
+            atomicAdd(p0, acc[j][0]); atomicAdd(p0 + 1, acc[j][1]);
+            atomicAdd(p1, acc[j][2]); atomicAdd(p1 + 1, acc[j][3]);
+        }
     }
     if (threadIdx.x < M) {
         float sacc = 0.f;
@@ -962,9 +983,10 @@ struct ScatterArgs {
     float* gplanes[S3G_MAX_LEVELS][6];
     float* d_xyz;                          // [P,3], += grid path
 };
+template <int LT>
 __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a) {
     const DNet& n = a.net;
-    const int L = n.L;
+    const int L = LT > 0 ? LT : n.L;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int FL = FD * L;
@@ -974,20 +996,22 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
         for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gi * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
         ph[3] = a.time;
         float dph[3] = {0.f, 0.f, 0.f};    // this lane's share of dL/dp_hat
-        for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int l = 0; l < (LT > 0 ? LT : S3G_MAX_LEVELS); ++l) {
+            if (LT == 0 && l >= L) break;
             AxisTap ax[4];
 #pragma unroll
             for (int d = 0; d < 4; ++d) ax[d] = axis_tap(ph[d], n.reso[l][d]);
             float v[6][4], s[6];
-            int o00[6], o01[6], o10[6], o11[6];
+            uint32_t o00[6], o01[6], o10[6], o11[6];      // unsigned 32-bit texel offsets: one IMAD.WIDE.U32 per address
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const int ca = comb_a(k), cb = comb_b(k);
                 const int W = n.reso[l][ca];
                 const float* pl = n.planes[l][k] + lane;
                 const int r0 = ax[cb].i0 * W, r1 = ax[cb].i1 * W;
-                o00[k] = (r0 + ax[ca].i0) * FD; o01[k] = (r0 + ax[ca].i1) * FD;
-                o10[k] = (r1 + ax[ca].i0) * FD; o11[k] = (r1 + ax[ca].i1) * FD;
+                o00[k] = (uint32_t)(r0 + ax[ca].i0) * FD; o01[k] = (uint32_t)(r0 + ax[ca].i1) * FD;
+                o10[k] = (uint32_t)(r1 + ax[ca].i0) * FD; o11[k] = (uint32_t)(r1 + ax[ca].i1) * FD;
                 v[k][0] = __ldg(pl + o00[k]); v[k][1] = __ldg(pl + o01[k]);
                 v[k][2] = __ldg(pl + o10[k]); v[k][3] = __ldg(pl + o11[k]);
             }
@@ -1014,11 +1038,13 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
                 const AxisTap& Y = ax[cb];
                 const float ds = df * pre[k] * suf[k];
                 float* gp = a.gplanes[l][k] + lane;
-                // a clamped neighbour carries weight 0 and is skipped
-                atomicAdd(gp + o00[k], (X.omf * Y.omf) * ds);
-                if (X.f != 0.f) atomicAdd(gp + o01[k], (X.f * Y.omf) * ds);
-                if (Y.f != 0.f) atomicAdd(gp + o10[k], (X.omf * Y.f) * ds);
-                if (X.f != 0.f && Y.f != 0.f) atomicAdd(gp + o11[k], (X.f * Y.f) * ds);
+                // a border-clamped neighbour carries weight exactly 0 and aliases a valid texel: adding
+                // 0.0 leaves it unchanged, so the four REDs are unconditional (no branches in the loop)
+                const float wx0 = X.omf * ds, wx1 = X.f * ds;
+                atomicAdd(gp + o00[k], wx0 * Y.omf);
+                atomicAdd(gp + o01[k], wx1 * Y.omf);
+                atomicAdd(gp + o10[k], wx0 * Y.f);
+                atomicAdd(gp + o11[k], wx1 * Y.f);
                 // d(sample)/d(ix), d(sample)/d(iy)
                 const float dsx = (v[k][1] - v[k][0]) * Y.omf + (v[k][3] - v[k][2]) * Y.f;
                 const float dsy = (v[k][2] - v[k][0]) * X.omf + (v[k][3] - v[k][1]) * X.f;

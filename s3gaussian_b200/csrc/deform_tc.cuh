@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const __grid_const
         const int n = e / K, k = e - n * K;
         const float v = n < N ? __ldg(p.W[l] + (size_t)n * K + k) : 0.f;
         uint32_t hi, lo;
-        split_tf32(v, hi, lo);
+        split_tf32_rna(v, hi, lo);
         const int ci = umma::canon_idx(n, k, K);
         dst[ci] = __uint_as_float(hi);
         dst[NP * K + ci] = __uint_as_float(lo);

@@ -58,7 +58,7 @@ for path in ([] if "--notest" in sys.argv else sorted(glob.glob(os.path.join(ROO
         print("   bwd:", " ".join(msg), f"| {cnt} param grads, worst {worst:.1e}")
 # timing at 2M with the default config
 if "--time" in sys.argv:
-    P = 2_000_000
+    P = int(os.environ.get("DEV_P", 2_000_000))
     st = syn.make_deform_state(0, weight_scale=0.2)
     net = deform_network(make_args(syn.DEFAULT_RESOLUTION, syn.DEFAULT_MULTIRES)); net.deformation_net.set_aabb(*[list(a) for a in syn.WAYMO_AABB])
     net.load_state_dict(st, strict=False); net = net.to(dev)

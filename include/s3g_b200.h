@@ -315,6 +315,21 @@ size_t s3g_plane_reg_workspace_bytes(int n, const s3g_plane_desc* planes);
 int s3g_plane_reg_forward(int n, const s3g_plane_desc* planes, double* total, void* workspace, void* stream);
 int s3g_plane_reg_backward(int n, const s3g_plane_desc* planes, const float* gscale, void* stream);
 
+/* ---- densify / prune row gather ------------------------------------------
+ * s3g_gather_rows  <- _prune_optimizer / cat_tensors_to_optimizer / prune_points / densification_postfix
+ *                     scene/gaussian_model.py:411-470 (boolean indexing + torch.cat per tensor)
+ * For every tensor t (HOST array of descriptors, n <= 32; src/dst are device pointers to [rows, row_floats]
+ * float32, dst has n_out rows):  dst[r] = src[src_index[r]] for r < n_kept or zero_new == 0, else 0.
+ * src_index: DEVICE int64[n_out], each value a valid source row. */
+typedef struct s3g_row_tensor {
+    const float* src;
+    float* dst;
+    int row_floats;
+    int zero_new;      /* 1 for optimizer state (exp_avg, exp_avg_sq): appended rows start at zero */
+} s3g_row_tensor;
+int s3g_gather_rows(int n, const s3g_row_tensor* tensors, int64_t n_out, int64_t n_kept, const int64_t* src_index,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,8 @@
 #
 #   oracle/_ref/diff_gaussian_rasterization/{__init__.py,_C*.so}   reference CUDA rasterizer, sm_100
 #   oracle/_ref/s3g_ref/scene/{hexplane,deformation,grid}.py       reference HexPlane + decoder (PyTorch)
-#   oracle/_ref/s3g_ref/utils/{graphics_utils,sh_utils,loss_utils}.py
+#   oracle/_ref/s3g_ref/scene/gaussian_model.py                    densify / prune methods (extracted with ast by the tests)
+#   oracle/_ref/s3g_ref/utils/{graphics_utils,sh_utils,loss_utils,general_utils}.py
 set -euo pipefail
 REF=${REF:-/root/reference}
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -25,8 +26,8 @@ DGR="$REF/submodules/depth-diff-gaussian-rasterization"
 mkdir -p "$OUT/diff_gaussian_rasterization" "$OUT/s3g_ref/scene" "$OUT/s3g_ref/utils"
 
 # --- python half (pure copies into the git-ignored install dir) -------------
-cp -f "$REF/scene/hexplane.py" "$REF/scene/deformation.py" "$REF/scene/grid.py" "$OUT/s3g_ref/scene/"
-cp -f "$REF/utils/graphics_utils.py" "$REF/utils/sh_utils.py" "$REF/utils/loss_utils.py" "$OUT/s3g_ref/utils/"
+cp -f "$REF/scene/hexplane.py" "$REF/scene/deformation.py" "$REF/scene/grid.py" "$REF/scene/gaussian_model.py" "$OUT/s3g_ref/scene/"
+cp -f "$REF/utils/graphics_utils.py" "$REF/utils/sh_utils.py" "$REF/utils/loss_utils.py" "$REF/utils/general_utils.py" "$OUT/s3g_ref/utils/"
 cp -f "$REF/arguments/__init__.py" "$OUT/s3g_ref/arguments_init.py"
 cp -f "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "s3g_densify_stats": (_I, [_I, _V, _V, _V, _V, _V, _V]),
     "s3g_image_loss_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "s3g_image_loss_forward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V]),
+    "s3g_gather_rows": (_I, [_I, _V, _I64, _I64, _V, _V]),
     "s3g_plane_reg_workspace_bytes": (_SZ, [_I, _V]),
     "s3g_plane_reg_forward": (_I, [_I, _V, _V, _V, _V]),
     "s3g_plane_reg_backward": (_I, [_I, _V, _V, _V]),
@@ -119,3 +120,8 @@ class PlaneDesc(C.Structure):
     """s3g_plane_desc (include/s3g_b200.h)."""
     _fields_ = [("plane", C.c_void_p), ("grad", C.c_void_p), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
                 ("w_smooth", C.c_float), ("w_l1", C.c_float)]
+
+
+class RowTensor(C.Structure):
+    """s3g_row_tensor (include/s3g_b200.h)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_floats", C.c_int), ("zero_new", C.c_int)]

@@ -926,4 +926,32 @@ int s3g_plane_reg_backward(int n, const s3g_plane_desc* planes, const float* gsc
     return S3G_OK;
 }
 
+// ---- densify / prune row gather ----------------------------------------------------------------
+int s3g_gather_rows(int n, const s3g_row_tensor* tensors, int64_t n_out, int64_t n_kept, const int64_t* src_index,
+                    void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n <= 0 || n > ROWS_MAX_TENSORS || !tensors) return fail(S3G_ERR_ARG, "gather_rows: 1..32 tensors expected");
+    if (n_out < 0 || n_kept < 0 || n_kept > n_out) return fail(S3G_ERR_ARG, "gather_rows: need 0 <= n_kept <= n_out");
+    if (n_out == 0) return S3G_OK;
+    if (!src_index) return fail(S3G_ERR_ARG, "gather_rows: null src_index");
+    RowArgs a;
+    a.count = n; a.n_out = n_out; a.n_kept = n_kept;
+    a.src_index = reinterpret_cast<const long long*>(src_index);
+    long long most = 0;
+    for (int i = 0; i < n; ++i) {
+        const s3g_row_tensor& t = tensors[i];
+        if (!t.src || !t.dst || t.row_floats <= 0) return fail(S3G_ERR_ARG, "gather_rows: null pointer or row_floats <= 0");
+        a.t[i] = RowTensor{t.src, t.dst, t.row_floats, t.zero_new};
+        most = std::max(most, (long long)n_out * t.row_floats);
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (most + 255) / 256;
+    const int gx = (int)std::min<long long>(want, (long long)sms * 8);
+    gather_rows_kernel<<<dim3(gx, n), 256, 0, stream>>>(a);
+    S3G_CUDA(cudaGetLastError(), "gather_rows launch");
+    return S3G_OK;
+}
+
 }  // extern "C"

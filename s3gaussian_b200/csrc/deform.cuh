@@ -244,11 +244,12 @@ __device__ __forceinline__ void sample_gaussian(const DNet& n, const float ph[4]
                 const int a = comb_a(k), b = comb_b(k);
                 const int W = n.reso[l][a];
                 const float* pl = n.planes[l][k] + lane;
+                // unsigned 32-bit texel offsets (planes are < 2^32 floats): one IMAD.WIDE.U32 per address
                 const int r0 = ax[dl][b].i0 * W, r1 = ax[dl][b].i1 * W;
-                v[dl][k][0] = __ldg(pl + (size_t)(r0 + ax[dl][a].i0) * FD);
-                v[dl][k][1] = __ldg(pl + (size_t)(r0 + ax[dl][a].i1) * FD);
-                v[dl][k][2] = __ldg(pl + (size_t)(r1 + ax[dl][a].i0) * FD);
-                v[dl][k][3] = __ldg(pl + (size_t)(r1 + ax[dl][a].i1) * FD);
+                v[dl][k][0] = __ldg(pl + (uint32_t)(r0 + ax[dl][a].i0) * FD);
+                v[dl][k][1] = __ldg(pl + (uint32_t)(r0 + ax[dl][a].i1) * FD);
+                v[dl][k][2] = __ldg(pl + (uint32_t)(r1 + ax[dl][a].i0) * FD);
+                v[dl][k][3] = __ldg(pl + (uint32_t)(r1 + ax[dl][a].i1) * FD);
             }
         }
 #pragma unroll

@@ -460,4 +460,39 @@ __global__ void __launch_bounds__(REG_THREADS) plane_reg_backward_kernel(const _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row gather for densify / prune (scene/gaussian_model.py:411-470: _prune_optimizer,
+// cat_tensors_to_optimizer, prune_points, densification_postfix).  The reference rebuilds each of the six
+// per-Gaussian parameters and their two Adam moments with boolean indexing + torch.cat, one tensor at a
+// time (~60 launches and as many temporaries).  Here every tensor is rebuilt by ONE launch:
+//   dst_t[r] = src_t[src_index[r]]                         for r < n_kept, and for parameters
+//   dst_t[r] = 0                                           for r >= n_kept when t is optimizer state
+// (rows >= n_kept are the appended clones / split children, whose moments start at zero).
+// ---------------------------------------------------------------------------------------------
+constexpr int ROWS_MAX_TENSORS = 32;
+struct RowTensor {
+    const float* src;
+    float* dst;
+    int row_floats;
+    int zero_new;
+};
+struct RowArgs {
+    RowTensor t[ROWS_MAX_TENSORS];
+    int count;
+    long long n_out, n_kept;
+    const long long* src_index;
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ RowArgs a) {
+    const RowTensor& t = a.t[blockIdx.y];
+    const long long total = a.n_out * t.row_floats;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long r = e / t.row_floats;
+        const int c = (int)(e - r * t.row_floats);
+        float v = 0.f;
+        if (r < a.n_kept || !t.zero_new) v = __ldg(t.src + __ldg(a.src_index + r) * t.row_floats + c);
+        t.dst[e] = v;
+    }
+}
+
 }  // namespace s3g

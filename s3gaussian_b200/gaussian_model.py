@@ -1,0 +1,341 @@
+"""Training state of the Gaussians: the part of the reference's ``GaussianModel``
+(scene/gaussian_model.py) that the training loop touches every iteration or every
+densification interval - parameters, optimizer, densification statistics, densify / prune.
+
+Same attribute and method names as the reference so ``train.py``-style loops read the same
+(``training_setup``, ``update_learning_rate``, ``add_densification_stats``, ``densify``, ``prune``,
+``prune_points``, ``reset_opacity``, ``compute_regulation`` ...).  What differs is how the work runs:
+
+* the optimizer is ``FusedAdam`` (one launch per step, optim.py) with the reference's eight groups
+  and learning rates (scene/gaussian_model.py:176-189);
+* densify / prune rebuild the six parameters, their twelve Adam moments and the four per-Gaussian
+  accumulators with ONE row-gather launch per operation (``s3g_gather_rows``) instead of boolean
+  indexing + ``torch.cat`` per tensor (gaussian_model.py:411-470); the small mask / index arithmetic
+  stays in torch;
+* ``prune`` does not call ``torch.cuda.empty_cache()`` (gaussian_model.py:672): nothing is freed to
+  the driver, so there is no allocator stall afterwards.
+
+Row order after every operation, Adam moments of kept / new rows, the random samples of
+``densify_and_split`` (same ``torch.normal`` call, so the same values for the same generator state)
+match the reference bit for bit (tests/test_gpu_train.py runs the reference's own methods side by side).
+
+Out of scope here: ``create_from_pcd`` (needs simple-knn's distCUDA2), .ply / checkpoint
+I/O.  CUDA only; no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from argparse import Namespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .optim import FusedAdam, add_densification_stats, get_expon_lr_func
+
+PARAM_GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")      # names of gaussian_model.py:176-186
+_ATTR = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity",
+         "scaling": "_scaling", "rotation": "_rotation"}
+
+
+def default_optimization_params(**over) -> Namespace:
+    """The fields of OptimizationParams the model reads (arguments/__init__.py:100-141)."""
+    d = dict(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
+             position_lr_max_steps=30_000, deformation_lr_init=0.000016, deformation_lr_final=0.0000016,
+             deformation_lr_delay_mult=0.01, grid_lr_init=0.00016, grid_lr_final=0.000016, feature_lr=0.0025,
+             opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001, percent_dense=0.01)
+    d.update(over)
+    return Namespace(**d)
+
+
+def inverse_sigmoid(x):
+    return torch.log(x / (1 - x))                # utils/general_utils.py:115-116
+
+
+def build_rotation(r):
+    """Unit-quaternion (w,x,y,z) rows -> rotation matrices (utils/general_utils.py:245-266)."""
+    q = r / torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])[:, None]
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.zeros((q.size(0), 3, 3), device=r.device)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - w * z)
+    R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y)
+    R[:, 2, 1] = 2 * (y * z + w * x)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def split_plan(selected: torch.Tensor):
+    """Row plan of densify_and_split + prune_points (gaussian_model.py:496-522): kept rows in order, then the
+    selected rows twice (``repeat(N, 1)`` with N = 2).  -> (src_index int64 [n_kept + 2 n_sel], n_kept, sel)."""
+    sel = torch.nonzero(selected, as_tuple=False).squeeze(1)
+    keep = torch.nonzero(~selected, as_tuple=False).squeeze(1)
+    return torch.cat((keep, sel, sel)), int(keep.numel()), sel
+
+
+class GaussianModel:
+    def __init__(self, sh_degree: int, args=None, deformation=None):
+        self.active_sh_degree = 0
+        self.max_sh_degree = sh_degree
+        if deformation is None and args is not None:
+            from .deformation import deform_network
+            deformation = deform_network(args)
+        self._deformation = deformation
+        e = torch.empty(0)
+        self._xyz = self._features_dc = self._features_rest = self._scaling = self._rotation = self._opacity = e
+        self.max_radii2D = self.xyz_gradient_accum = self.denom = self._deformation_accum = e
+        self._deformation_table = e
+        self.optimizer = None
+        self.percent_dense = 0
+        self.spatial_lr_scale = 0
+        self.scaling_activation = torch.exp
+        self.scaling_inverse_activation = torch.log
+        self.opacity_activation = torch.sigmoid
+        self.inverse_opacity_activation = inverse_sigmoid
+        self.rotation_activation = torch.nn.functional.normalize
+
+    # ---- construction ---------------------------------------------------------------------------
+    def create_from_tensors(self, xyz, features_dc, features_rest, scaling, rotation, opacity, spatial_lr_scale=1.0):
+        """The tail of create_from_pcd (gaussian_model.py:141-169) for already-initialised raw parameters
+        (log-scales, raw quaternions, logit opacities)."""
+        dev = xyz.device
+        if dev.type != "cuda":
+            raise RuntimeError("GaussianModel: CUDA tensors only (there is no CPU path)")
+        self.spatial_lr_scale = spatial_lr_scale
+        mk = lambda t: nn.Parameter(t.detach().clone().float().contiguous().requires_grad_(True))
+        self._xyz, self._features_dc, self._features_rest = mk(xyz), mk(features_dc), mk(features_rest)
+        self._scaling, self._rotation, self._opacity = mk(scaling), mk(rotation), mk(opacity)
+        if self._deformation is not None:
+            self._deformation = self._deformation.to(dev)
+        P = xyz.shape[0]
+        self.max_radii2D = torch.zeros(P, device=dev)
+        self._deformation_table = torch.ones(P, dtype=torch.bool, device=dev)
+        return self
+
+    def create_from_pcd(self, *a, **k):
+        raise NotImplementedError("create_from_pcd needs simple-knn's distCUDA2 (SURVEY 8f f-4); "
+                                  "initialise the tensors and call create_from_tensors")
+
+    # ---- the accessors render() and the loop read (gaussian_model.py:113-140) --------------------
+    @property
+    def get_scaling(self):
+        return self.scaling_activation(self._scaling)
+
+    @property
+    def get_rotation(self):
+        return self.rotation_activation(self._rotation)
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    @property
+    def get_opacity(self):
+        return self.opacity_activation(self._opacity)
+
+    def get_covariance(self, scaling_modifier=1):
+        from .gaussian_renderer import GaussianModelLite
+        return GaussianModelLite.get_covariance(self, scaling_modifier)
+
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    def compute_regulation(self, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight):
+        from .regulation import compute_regulation
+        return compute_regulation(self._deformation.deformation_net.grid.grids, time_smoothness_weight,
+                                  l1_time_planes_weight, plane_tv_weight)
+
+    # ---- optimizer (gaussian_model.py:170-215) ----------------------------------------------------
+    def training_setup(self, training_args):
+        dev = self._xyz.device
+        P = self._xyz.shape[0]
+        self.percent_dense = training_args.percent_dense
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=dev)
+        self.denom = torch.zeros((P, 1), device=dev)
+        self._deformation_accum = torch.zeros((P, 3), device=dev)
+        s = self.spatial_lr_scale
+        groups = [{"params": [self._xyz], "lr": training_args.position_lr_init * s, "name": "xyz"}]
+        if self._deformation is not None:
+            groups += [{"params": list(self._deformation.get_mlp_parameters()),
+                        "lr": training_args.deformation_lr_init * s, "name": "deformation"},
+                       {"params": list(self._deformation.get_grid_parameters()),
+                        "lr": training_args.grid_lr_init * s, "name": "grid"}]
+        groups += [{"params": [self._features_dc], "lr": training_args.feature_lr, "name": "f_dc"},
+                   {"params": [self._features_rest], "lr": training_args.feature_lr / 20.0, "name": "f_rest"},
+                   {"params": [self._opacity], "lr": training_args.opacity_lr, "name": "opacity"},
+                   {"params": [self._scaling], "lr": training_args.scaling_lr, "name": "scaling"},
+                   {"params": [self._rotation], "lr": training_args.rotation_lr, "name": "rotation"}]
+        self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        self.xyz_scheduler_args = get_expon_lr_func(training_args.position_lr_init * s, training_args.position_lr_final * s,
+                                                    lr_delay_mult=training_args.position_lr_delay_mult,
+                                                    max_steps=training_args.position_lr_max_steps)
+        self.deformation_scheduler_args = get_expon_lr_func(training_args.deformation_lr_init * s,
+                                                            training_args.deformation_lr_final * s,
+                                                            lr_delay_mult=training_args.deformation_lr_delay_mult,
+                                                            max_steps=training_args.position_lr_max_steps)
+        self.grid_scheduler_args = get_expon_lr_func(training_args.grid_lr_init * s, training_args.grid_lr_final * s,
+                                                     lr_delay_mult=training_args.deformation_lr_delay_mult,
+                                                     max_steps=training_args.position_lr_max_steps)
+
+    def update_learning_rate(self, iteration):
+        """gaussian_model.py:203-215 as written upstream: the xyz and grid groups follow their schedules; the
+        'deformation' group's schedule is evaluated but not assigned (the elif branch only computes lr)."""
+        for group in self.optimizer.param_groups:
+            if group["name"] == "xyz":
+                group["lr"] = self.xyz_scheduler_args(iteration)
+            if "grid" in group["name"]:
+                group["lr"] = self.grid_scheduler_args(iteration)
+            elif group["name"] == "deformation":
+                self.deformation_scheduler_args(iteration)
+
+    # ---- per-iteration statistics (train.py:489-491, gaussian_model.py:693-695) --------------------
+    def add_densification_stats(self, viewspace_point_tensor, update_filter):
+        scratch = torch.zeros_like(self.max_radii2D)
+        add_densification_stats(viewspace_point_tensor.contiguous(), update_filter.to(torch.int32), self.xyz_gradient_accum,
+                                self.denom, scratch)
+
+    def densification_step(self, viewspace_point_tensor_grad, radii):
+        """max_radii2D update + add_densification_stats with visibility_filter = radii > 0, one launch."""
+        add_densification_stats(viewspace_point_tensor_grad.contiguous(), radii, self.xyz_gradient_accum, self.denom,
+                                self.max_radii2D)
+
+    # ---- row surgery --------------------------------------------------------------------------------
+    def _group(self, name):
+        for g in self.optimizer.param_groups:
+            if g["name"] == name:
+                return g
+        raise KeyError(name)
+
+    def _rebuild(self, src_index: torch.Tensor, n_kept: int, keep_accumulators: bool):
+        """Every per-Gaussian tensor <- rows ``src_index`` of itself; rows >= n_kept are new (Adam moments zero)."""
+        lib = _lib.load()
+        dev = self._xyz.device
+        n_out = int(src_index.numel())
+        src_index = src_index.to(torch.int64).contiguous()
+        descs, new_params, new_states, hold = [], {}, {}, []
+
+        def add(src, zero_new):
+            src = src.contiguous()
+            rf = math.prod(src.shape[1:])
+            dst = torch.empty((n_out, *src.shape[1:]), device=dev, dtype=torch.float32)
+            descs.append(_lib.RowTensor(src.data_ptr(), dst.data_ptr(), int(rf), 1 if zero_new else 0))
+            hold.append(src)
+            return dst
+        for name in PARAM_GROUPS:
+            p = getattr(self, _ATTR[name])
+            new_params[name] = add(p.data, False)
+            st = self.optimizer.state.get(p, None) if self.optimizer is not None else None
+            if st:
+                new_states[name] = (st["step"], add(st["exp_avg"], True), add(st["exp_avg_sq"], True))
+        acc = None
+        if keep_accumulators:
+            acc = [add(self.xyz_gradient_accum, False), add(self.denom, False), add(self._deformation_accum, False),
+                   add(self.max_radii2D.unsqueeze(1), False)]
+        if n_out > 0:
+            arr = (_lib.RowTensor * len(descs))(*descs)
+            _lib.check(lib.s3g_gather_rows(len(descs), arr, n_out, int(n_kept), src_index.data_ptr(),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "s3g_gather_rows")
+        for name in PARAM_GROUPS:
+            old = getattr(self, _ATTR[name])
+            newp = nn.Parameter(new_params[name].requires_grad_(True))
+            if self.optimizer is not None:
+                group = self._group(name)
+                self.optimizer.state.pop(old, None)
+                group["params"][0] = newp
+                if name in new_states:
+                    step, m, v = new_states[name]
+                    self.optimizer.state[newp] = {"step": step, "exp_avg": m, "exp_avg_sq": v}
+            setattr(self, _ATTR[name], newp)
+        self._deformation_table = self._deformation_table[src_index]
+        if keep_accumulators:
+            self.xyz_gradient_accum, self.denom, self._deformation_accum = acc[0], acc[1], acc[2]
+            self.max_radii2D = acc[3].squeeze(1)
+        else:       # densification_postfix resets them (gaussian_model.py:490-494)
+            self.xyz_gradient_accum = torch.zeros((n_out, 1), device=dev)
+            self._deformation_accum = torch.zeros((n_out, 3), device=dev)
+            self.denom = torch.zeros((n_out, 1), device=dev)
+            self.max_radii2D = torch.zeros(n_out, device=dev)
+
+    def prune_points(self, mask):
+        """gaussian_model.py:441-455."""
+        keep = torch.nonzero(~mask, as_tuple=False).squeeze(1)
+        self._rebuild(keep, int(keep.numel()), keep_accumulators=True)
+
+    def densify_and_clone(self, grads, grad_threshold, scene_extent):
+        """gaussian_model.py:524-563: small Gaussians with a large view-space gradient are duplicated in place."""
+        selected = torch.logical_and(torch.norm(grads, dim=-1) >= grad_threshold,
+                                     torch.max(self.get_scaling, dim=1).values <= self.percent_dense * scene_extent)
+        P = self._xyz.shape[0]
+        sel = torch.nonzero(selected, as_tuple=False).squeeze(1)
+        self._rebuild(torch.cat((torch.arange(P, device=sel.device), sel)), P, keep_accumulators=False)
+
+    def densify_and_split(self, grads, grad_threshold, scene_extent, N=2):
+        """gaussian_model.py:496-522: large Gaussians with a large gradient are replaced by N = 2 samples of
+        themselves, 1.6x smaller."""
+        if N != 2:
+            raise NotImplementedError("densify_and_split: the reference calls it with N = 2 only")
+        P = self._xyz.shape[0]
+        dev = self._xyz.device
+        padded_grad = torch.zeros(P, device=dev)
+        padded_grad[:grads.shape[0]] = grads.squeeze()
+        selected = torch.logical_and(padded_grad >= grad_threshold,
+                                     torch.max(self.get_scaling, dim=1).values > self.percent_dense * scene_extent)
+        if not selected.any():
+            return
+        with torch.no_grad():
+            stds = self.get_scaling[selected].repeat(N, 1)
+            samples = torch.normal(mean=torch.zeros((stds.size(0), 3), device=dev), std=stds)
+            rots = build_rotation(self._rotation[selected]).repeat(N, 1, 1)
+            new_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + self.get_xyz[selected].repeat(N, 1)
+            new_scaling = self.scaling_inverse_activation(self.get_scaling[selected].repeat(N, 1) / (0.8 * N))
+            src_index, n_kept, _ = split_plan(selected)
+            self._rebuild(src_index, n_kept, keep_accumulators=False)
+            self._xyz.data[n_kept:] = new_xyz
+            self._scaling.data[n_kept:] = new_scaling
+
+    def densify(self, max_grad, min_opacity, extent, max_screen_size, *unused, **unused_kw):
+        """gaussian_model.py:674-679."""
+        grads = self.xyz_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        with torch.no_grad():
+            self.densify_and_clone(grads, max_grad, extent)
+        self.densify_and_split(grads, max_grad, extent)
+
+    def prune(self, max_grad, min_opacity, extent, max_screen_size):
+        """gaussian_model.py:661-672 (without the empty_cache() call)."""
+        with torch.no_grad():
+            prune_mask = (self.get_opacity < min_opacity).squeeze()
+            if max_screen_size:
+                big_points_vs = self.max_radii2D > max_screen_size
+                big_points_ws = self.get_scaling.max(dim=1).values > 0.1 * extent
+                prune_mask = torch.logical_or(torch.logical_or(prune_mask, big_points_vs), big_points_ws)
+            self.prune_points(prune_mask)
+
+    def replace_tensor_to_optimizer(self, tensor, name):
+        """gaussian_model.py:397-409: new parameter values, Adam moments reset to zero, step kept."""
+        group = self._group(name)
+        old = group["params"][0]
+        st = self.optimizer.state.pop(old, None)
+        newp = nn.Parameter(tensor.detach().clone().contiguous().requires_grad_(True))
+        group["params"][0] = newp
+        if st is not None:
+            st["exp_avg"] = torch.zeros_like(newp)
+            st["exp_avg_sq"] = torch.zeros_like(newp)
+            self.optimizer.state[newp] = st
+        return {name: newp}
+
+    def reset_opacity(self):
+        """gaussian_model.py:350-353."""
+        with torch.no_grad():
+            new = inverse_sigmoid(torch.min(self.get_opacity, torch.ones_like(self.get_opacity) * 0.01))
+        self._opacity = self.replace_tensor_to_optimizer(new, "opacity")["opacity"]

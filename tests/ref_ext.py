@@ -128,3 +128,43 @@ def load_ref_loss_utils():
         sys.modules["utils"] = m
     from utils import loss_utils
     return loss_utils
+
+
+# ---- the reference's GaussianModel methods (oracle/_ref/s3g_ref/scene/gaussian_model.py) ----
+def gaussian_model_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "scene", "gaussian_model.py")) and \
+        os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "utils", "general_utils.py"))
+
+
+def load_ref_gaussian_model_class():
+    """A class carrying the UNMODIFIED method bodies of the reference's GaussianModel that the training loop
+    uses for densification (properties, densify*, prune*, *_optimizer, reset_opacity, add_densification_stats).
+    The module itself cannot be imported (simple_knn, open3d, plyfile): the FunctionDefs are taken from the
+    source with ast and compiled as they are; build_rotation / inverse_sigmoid come the same way from
+    utils/general_utils.py."""
+    import ast
+    import torch
+    base = os.path.join(REF_DIR, "s3g_ref")
+    ns = {"torch": torch, "nn": torch.nn, "np": np}
+
+    def grab(path, names, into):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), into)
+    grab(os.path.join(base, "utils", "general_utils.py"), {"build_rotation", "inverse_sigmoid"}, ns)
+    methods = {"get_scaling", "get_rotation", "get_xyz", "get_features", "get_opacity", "densify", "densify_and_clone",
+               "densify_and_split", "densification_postfix", "cat_tensors_to_optimizer", "prune_points",
+               "_prune_optimizer", "prune", "add_densification_stats", "reset_opacity", "replace_tensor_to_optimizer"}
+    cls_ns = dict(ns)
+    grab(os.path.join(base, "scene", "gaussian_model.py"), methods, cls_ns)
+
+    class RefGaussianModel:
+        scaling_activation = staticmethod(torch.exp)
+        scaling_inverse_activation = staticmethod(torch.log)
+        opacity_activation = staticmethod(torch.sigmoid)
+        rotation_activation = staticmethod(torch.nn.functional.normalize)
+    for m in methods:
+        setattr(RefGaussianModel, m, cls_ns[m])
+    # the extracted functions look their globals up in cls_ns (torch, nn, build_rotation, inverse_sigmoid)
+    return RefGaussianModel

@@ -234,3 +234,154 @@ def test_plane_regulation_full_size_and_adam_on_channels_last_planes(built_lib):
     torch.optim.Adam([{"params": clones, "lr": 1.6e-3, "name": "grid"}], lr=0.0, eps=1e-15).step()
     for c, p in zip(clones, planes):
         assert rel(p, c) < 2e-6
+
+
+# ---- densify / prune against the reference's own methods ---------------------------------------
+def _pair_of_models(P, seed):
+    """Our GaussianModel and the reference's method bodies over identical tensors, optimizer state and
+    densification statistics."""
+    import ref_ext
+    from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params, PARAM_GROUPS, _ATTR
+    Ref = ref_ext.load_ref_gaussian_model_class()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    xyz = r(P, 3) * 10
+    scaling = torch.log(torch.exp(r(P, 3) * 0.9 - 2.0))          # scales straddle percent_dense * extent
+    ours = GaussianModel(3).create_from_tensors(xyz, r(P, 1, 3), r(P, 15, 3) * 0.1, scaling, r(P, 4), r(P, 1) * 2)
+    opt_args = default_optimization_params()
+    ours.training_setup(opt_args)
+    ref = Ref()
+    for name in PARAM_GROUPS:
+        setattr(ref, _ATTR[name], torch.nn.Parameter(getattr(ours, _ATTR[name]).detach().clone().requires_grad_(True)))
+    ref.percent_dense = opt_args.percent_dense
+    ref._deformation_table = torch.ones(P, dtype=torch.bool, device=DEV)
+    ref.optimizer = torch.optim.Adam([{"params": [getattr(ref, _ATTR[n])], "lr": gr["lr"], "name": n}
+                                      for n, gr in ((n, ours._group(n)) for n in PARAM_GROUPS)], lr=0.0, eps=1e-15)
+    # two optimizer steps on the reference, then copy its state into ours bit for bit
+    for _ in range(2):
+        for n in PARAM_GROUPS:
+            p = getattr(ref, _ATTR[n])
+            p.grad = torch.randn(p.shape, device=DEV, generator=g) * 0.01
+        ref.optimizer.step()
+    for n in PARAM_GROUPS:
+        po, pr = getattr(ours, _ATTR[n]), getattr(ref, _ATTR[n])
+        po.data.copy_(pr.data)
+        st = ref.optimizer.state[pr]
+        ours.optimizer.state[po] = {"step": st["step"].clone(), "exp_avg": st["exp_avg"].clone(),
+                                    "exp_avg_sq": st["exp_avg_sq"].clone()}
+        pr.grad = None
+    acc = torch.rand(P, 1, device=DEV, generator=g) * 6e-4
+    den = torch.randint(0, 4, (P, 1), device=DEV, generator=g).float()        # zeros -> nan -> 0 path
+    mr = torch.randint(0, 40, (P,), device=DEV, generator=g).float()
+    for m in (ours, ref):
+        m.xyz_gradient_accum, m.denom, m.max_radii2D = acc.clone(), den.clone(), mr.clone()
+        m._deformation_accum = torch.zeros(P, 3, device=DEV)
+    return ours, ref
+
+
+def _assert_same_state(ours, ref, what):
+    from s3gaussian_b200.gaussian_model import PARAM_GROUPS, _ATTR
+    for n in PARAM_GROUPS:
+        po, pr = getattr(ours, _ATTR[n]), getattr(ref, _ATTR[n])
+        assert po.shape == pr.shape, (what, n, po.shape, pr.shape)
+        assert torch.equal(po.data, pr.data), (what, n)
+        so, sr = ours.optimizer.state.get(po), ref.optimizer.state.get(pr)
+        assert (so is None) == (sr is None), (what, n)
+        if so is not None:
+            assert torch.equal(so["exp_avg"], sr["exp_avg"]) and torch.equal(so["exp_avg_sq"], sr["exp_avg_sq"]), (what, n)
+            assert float(so["step"]) == float(sr["step"])
+        assert ours._group(n)["params"][0] is po
+    for a in ("xyz_gradient_accum", "denom", "max_radii2D", "_deformation_accum", "_deformation_table"):
+        assert torch.equal(getattr(ours, a), getattr(ref, a)), (what, a)
+
+
+def test_densify_prune_reset_match_reference_methods(built_lib):
+    import ref_ext
+    if not ref_ext.gaussian_model_available():
+        pytest.skip("oracle/_ref/s3g_ref/scene/gaussian_model.py not present (run oracle/build_ref.sh)")
+    P = 50000
+    ours, ref = _pair_of_models(P, 7)
+    extent = 20.0
+    # densify (clone + split), identical generator state for the torch.normal inside densify_and_split
+    torch.manual_seed(123)
+    ours.densify(0.0002, 0.005, extent, None)
+    torch.manual_seed(123)
+    ref.densify(0.0002, 0.005, extent, None, 5, 5, None, None, None)
+    assert ours._xyz.shape[0] > P                      # the case is not degenerate
+    _assert_same_state(ours, ref, "densify")
+    n1 = ours._xyz.shape[0]
+    # statistics for the next round (ours: fused kernel; reference: its own method + train.py:490)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    radii = torch.randint(0, 45, (n1,), device=DEV, generator=g, dtype=torch.int32)
+    radii[torch.rand(n1, device=DEV, generator=g) < 0.3] = 0
+    vgrad = torch.randn(n1, 3, device=DEV, generator=g) * 1e-3
+    ours.densification_step(vgrad, radii)
+    vis = radii > 0
+    ref.max_radii2D[vis] = torch.max(ref.max_radii2D[vis], radii[vis])
+    ref.add_densification_stats(vgrad, vis)
+    assert torch.equal(ours.max_radii2D, ref.max_radii2D) and torch.equal(ours.denom, ref.denom)
+    assert rel(ours.xyz_gradient_accum, ref.xyz_gradient_accum) < 1e-6
+    ours.xyz_gradient_accum = ref.xyz_gradient_accum.clone()       # 1-ulp differences of the norm: re-sync for bit tests
+    # prune with a screen-size limit (all three criteria)
+    ours.prune(0.0002, 0.005, extent, 20)
+    ref.prune(0.0002, 0.005, extent, 20)
+    assert ours._xyz.shape[0] < n1
+    _assert_same_state(ours, ref, "prune")
+    # opacity reset: values, zeroed moments, kept step
+    ours.reset_opacity()
+    ref.reset_opacity()
+    _assert_same_state(ours, ref, "reset_opacity")
+    # an optimizer step still works on the rebuilt parameters and matches torch.optim.Adam
+    from s3gaussian_b200.gaussian_model import PARAM_GROUPS, _ATTR
+    for n in PARAM_GROUPS:
+        po, pr = getattr(ours, _ATTR[n]), getattr(ref, _ATTR[n])
+        gr = torch.randn(po.shape, device=DEV, generator=g) * 0.01
+        po.grad, pr.grad = gr.clone(), gr.clone()
+    ours.optimizer.step()
+    ref.optimizer.step()
+    for n in PARAM_GROUPS:
+        assert rel(getattr(ours, _ATTR[n]), getattr(ref, _ATTR[n])) < 2e-6, n
+    # split with nothing selected returns without touching anything (gaussian_model.py:507-508)
+    before = ours._xyz.data_ptr()
+    ours.densify_and_split(torch.zeros(ours._xyz.shape[0], 1, device=DEV), 1.0, extent)
+    assert ours._xyz.data_ptr() == before
+
+
+def test_training_loop_with_model_render_loss_and_densify(built_lib):
+    """The pieces together the way train.py drives them: render -> fused loss -> backward -> stats -> densify/prune
+    every few iterations -> Adam; checks that it runs, the loss goes down and the point count changes."""
+    from s3gaussian_b200 import losses, synthetic as syn
+    from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params
+    from s3gaussian_b200.gaussian_renderer import render, PipelineParams
+    cloud = syn.make_cloud(30000, seed=3)
+    cams = syn.waymo_ring(480, 320, frames=4)
+    pc = GaussianModel(3).create_from_tensors(cloud.xyz.to(DEV), cloud.features_dc.to(DEV), cloud.features_rest.to(DEV),
+                                              cloud.scaling.to(DEV), cloud.rotation.to(DEV), cloud.opacity.to(DEV))
+    pc.active_sh_degree = 3
+    pc.training_setup(default_optimization_params())
+    bg = torch.zeros(3, device=DEV)
+    pipe = PipelineParams()
+    pipe.convert_SHs_python = False
+    with torch.no_grad():
+        targets = [(render(c, pc, pipe, bg, stage="coarse")["render"] * 0.5 + 0.25).clone() for c in cams[:3]]
+        tdepth = [torch.full((1, 320, 480), 20.0, device=DEV) for _ in cams[:3]]
+    first, last = {}, {}
+    sizes = set()
+    for it in range(1, 31):
+        cam = (it - 1) % 3
+        pc.update_learning_rate(it)
+        out = render(cams[cam], pc, pipe, bg, stage="coarse")
+        loss = losses.training_loss(out["render"], targets[cam], out["depth"], tdepth[cam])
+        loss.backward()
+        with torch.no_grad():
+            pc.densification_step(out["viewspace_points"].grad, out["radii"])
+            if it % 10 == 0:
+                pc.densify(2e-6, 0.005, 30.0, None)
+                pc.prune(2e-6, 0.005, 30.0, None)
+            sizes.add(pc.get_xyz.shape[0])
+        pc.optimizer.step()
+        pc.optimizer.zero_grad(set_to_none=True)
+        first.setdefault(cam, loss.item())
+        last[cam] = loss.item()
+    assert all(last[c] < first[c] for c in first), (first, last)
+    assert len(sizes) > 1

@@ -62,3 +62,44 @@ def test_expon_lr_schedule():
     assert f(-1) == 0.0 and get_expon_lr_func(0.0, 0.0)(5) == 0.0
     d = get_expon_lr_func(1.0, 1.0, lr_delay_steps=100, lr_delay_mult=0.1)
     assert d(0) == pytest.approx(0.1) and d(100) == pytest.approx(1.0) and 0.1 < d(50) < 1.0
+
+
+def test_split_plan_row_order():
+    """kept rows in order, then the selected rows twice - the order densify_and_split + prune_points produce
+    (scene/gaussian_model.py:496-522)."""
+    from s3gaussian_b200.gaussian_model import split_plan
+    sel = torch.tensor([False, True, False, False, True, False])
+    src, n_kept, idx = split_plan(sel)
+    assert n_kept == 4 and idx.tolist() == [1, 4]
+    assert src.tolist() == [0, 2, 3, 5, 1, 4, 1, 4]
+    # the same thing spelled the reference's way on a value tensor
+    x = torch.arange(6.0)
+    cat = torch.cat((x, x[sel].repeat(2)))
+    pruned = cat[~torch.cat((sel, torch.zeros(2 * int(sel.sum()), dtype=torch.bool)))]
+    assert torch.equal(pruned, x[src])
+
+
+def test_gaussian_model_rejects_cpu_and_exposes_reference_names(built_lib):
+    from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params
+    m = GaussianModel(3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.create_from_tensors(torch.zeros(4, 3), torch.zeros(4, 1, 3), torch.zeros(4, 15, 3), torch.zeros(4, 3),
+                              torch.zeros(4, 4), torch.zeros(4, 1))
+    with pytest.raises(NotImplementedError):
+        m.create_from_pcd(None, 1.0)
+    for name in ("training_setup", "update_learning_rate", "add_densification_stats", "densify", "prune", "prune_points",
+                 "densify_and_clone", "densify_and_split", "reset_opacity", "replace_tensor_to_optimizer",
+                 "compute_regulation", "oneupSHdegree", "get_covariance"):
+        assert callable(getattr(m, name))
+    a = default_optimization_params()
+    assert a.position_lr_init == 0.00016 and a.percent_dense == 0.01 and a.opacity_lr == 0.05
+
+
+def test_gather_rows_argument_checks(built_lib):
+    import ctypes as C
+    from s3gaussian_b200 import _lib
+    lib = _lib.load()
+    assert lib.s3g_gather_rows(0, None, 1, 1, None, None) == -1
+    t = (_lib.RowTensor * 1)(_lib.RowTensor(1, 1, 3, 0))
+    assert lib.s3g_gather_rows(1, t, 4, 5, None, None) == -1          # n_kept > n_out
+    assert lib.s3g_gather_rows(1, t, 0, 0, None, None) == 0           # nothing to do

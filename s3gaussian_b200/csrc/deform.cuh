@@ -26,7 +26,8 @@
 namespace s3g {
 
 constexpr int DT = 64;            // Gaussians per tile
-constexpr int DTHREADS = 256;
+constexpr int DTHREADS = 512;        // 16 warps: the tile kernels run one CTA per SM (shared memory), so the
+                                     // only latency hiding is warps within the CTA
 constexpr int HWID = 64;          // hidden width (net_width)
 constexpr int HS = HWID + 4;      // smem row stride of 64-wide tiles (== 4 mod 32: conflict-free fragments)
 constexpr int FD = 32;            // features per plane
@@ -138,24 +139,26 @@ struct WPipe {
 };
 
 // out[g][n] = act_out( sum_k act_in(in[g][k]) * W[n][k] + b[n] ),  g < 64, n < N (N = 64 or 48).
-// 8 warps: (warp & 3) picks 16 rows, (warp >> 2) picks half of the columns.
+// 16 warps: (warp & 3) picks 16 rows, (warp >> 2) picks 16 of the columns (N = 48: the last group idles).
 // sIn / sOut / sW are distinct smem regions; ends with a __syncthreads().
 template <int K, int N, bool RELU_IN, bool RELU_OUT>
 __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPipe& pipe,
                                             const float* __restrict__ bg, float* sOut, int outStride) {
     constexpr int WS = K + 4;
-    constexpr int NTW = N / 16;          // n-tiles (of 8) per warp
+    constexpr int NTW = 2;               // n-tiles (of 8) per warp
+    static_assert(N % 16 == 0 && N <= 64, "tile_linear: N in {16, 32, 48, 64}");
     const float* sW = pipe.acquire();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = (warp & 3) * 16;
-    const int c0 = (warp >> 2) * (N / 2);
+    const int c0 = (warp >> 2) * 16;
+    const bool active = c0 < N;
     float acc[NTW][4];
 #pragma unroll
     for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     const float* rowA = sIn + (r0 + g) * inStride + t;
     const float* rowB = sIn + (r0 + g + 8) * inStride + t;
 #pragma unroll 4
-    for (int k0 = 0; k0 < K; k0 += 8) {
+    for (int k0 = 0; active && k0 < K; k0 += 8) {
         float a[4] = {rowA[k0], rowB[k0], rowA[k0 + 4], rowB[k0 + 4]};
         uint32_t ah[4], al[4];
 #pragma unroll
@@ -174,6 +177,7 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
     }
 #pragma unroll
     for (int j = 0; j < NTW; ++j) {
+        if (!active) break;
         const int col = c0 + 8 * j + 2 * t;
         const float b0 = __ldg(bg + col), b1 = __ldg(bg + col + 1);
         float v0 = acc[j][0] + b0, v1 = acc[j][1] + b1, v2 = acc[j][2] + b0, v3 = acc[j][3] + b1;
@@ -191,7 +195,7 @@ __device__ __forceinline__ void tile_small_out(const float* sIn, int inStride, c
                                                const float* __restrict__ bg, int k, float* sOut,
                                                int outStride, int outCol) {
     const int g = threadIdx.x >> 2, o = threadIdx.x & 3;
-    if (o < k) {
+    if (o < k && g < DT) {
         const float* in = sIn + g * inStride;
         const float* w = Wg + o * HWID;
         float s = 0.f;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_forward_kernel(const __gri
         {
             const int g = tid >> 2, c = tid & 3;
             const int gi = g0 + g;
-            if (gi < a.P) {
+            if (g < DT && gi < a.P) {
                 const float* S = sm.S + g * 16;
                 if (c < 3) {
                     const float p = sm.X[g * 4 + c];
@@ -500,11 +504,12 @@ template <int K, int N, int MODE>
 __device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WPipe& pipe, float* sOut,
                                               int outStride, const float* sMask, int maskStride) {
     constexpr int WS = K + 4;
-    constexpr int NTW = K / 16;          // output n-tiles (of 8) per warp
+    constexpr int NTW = K / 32;          // output n-tiles (of 8) per warp: 4 column groups of K/4
+    static_assert(K % 32 == 0, "tile_linear_T: K must be a multiple of 32");
     const float* sW = pipe.acquire();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = (warp & 3) * 16;
-    const int c0 = (warp >> 2) * (K / 2);
+    const int c0 = (warp >> 2) * (K / 4);
     float acc[NTW][4];
 #pragma unroll
     for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
@@ -551,8 +556,8 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
                                          float* __restrict__ gW, float* __restrict__ gb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     constexpr int TN = NIN / 8;
-    constexpr int NT = 4;                        // n-tiles per work item: the delta fragment is split once for all of them
-    static_assert(TN % NT == 0, "dw_accum: NIN must be a multiple of 32");
+    constexpr int NT = 2;                        // n-tiles per work item: the delta fragment is split once for both
+    static_assert(TN % NT == 0, "dw_accum: NIN must be a multiple of 16");
     constexpr int ITEMS = (M / 16) * (TN / NT);
     for (int item = warp; item < ITEMS; item += DTHREADS / 32) {
         const int m0 = (item / (TN / NT)) * 16, n0 = (item % (TN / NT)) * (8 * NT);

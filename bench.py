@@ -479,6 +479,59 @@ def main_fine(a, rank, world, local, dev):
     ms_res = timed(step_resident, a.steps, max(a.warmup, 3))
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, a.steps, 3)
+    # ---- whole fine-stage training iteration (N == 1): render + every loss term of train.py:395-425 incl. SSIM and
+    # the plane regularisers + backward + densify stats + Adam over Gaussians, planes and decoder ------------------
+    train_it = None
+    if world == 1 and not a.no_train_iteration:
+        acc, den, maxr = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, device=dev)
+        groups = [{"params": [v], "lr": 1e-7, "name": str(i)} for i, v in enumerate(leaves)]
+        if a.impl == "ours":
+            from s3gaussian_b200 import losses, optim
+            opt = optim.FusedAdam(groups, lr=0.0, eps=1e-15)
+
+            def full_loss(out):
+                return (losses.training_loss(out["render"], img_d, out["depth"], dep_d) +
+                        0.001 * ((out["feat"] - feat_d) ** 2).mean() + 0.001 * out["dx"].abs().mean() +
+                        0.001 * out["dshs"].abs().mean() + pc.compute_regulation(0.01, 0.0001, 0.0001))
+
+            def stats(out):
+                optim.add_densification_stats(out["viewspace_points"].grad, out["radii"], acc, den, maxr)
+            what = "render(fine) + fused L1/SSIM/depth loss + feat/dx/dshs terms + fused plane regularisers + backward + fused stats + FusedAdam"
+        else:
+            opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+            lu = ref_ext.load_ref_loss_utils() if ref_ext.loss_utils_available() else None
+            reg = ref_ext.load_ref_compute_regulation() if ref_ext.regulation_available() else None
+
+            def full_loss(out):
+                base = (out["render"] - img_d).abs().mean() + 0.5 * ((out["depth"] - dep_d) ** 2).mean() if lu is None else \
+                    lu.l1_loss(out["render"], img_d) + 0.5 * lu.compute_depth("l2", out["depth"], dep_d) + \
+                    0.2 * (1.0 - lu.ssim(out["render"].unsqueeze(0), img_d.unsqueeze(0)))
+                loss = base + 0.001 * ((out["feat"] - feat_d) ** 2).mean() + 0.001 * out["dx"].abs().mean() + \
+                    0.001 * out["dshs"].abs().mean()
+                if reg is not None:
+                    loss = loss + reg(stack.net, 0.01, 0.0001, 0.0001)
+                return loss
+
+            def stats(out):
+                vis = out["radii"] > 0
+                maxr[vis] = torch.max(maxr[vis], out["radii"][vis])
+                acc[vis] += torch.norm(out["viewspace_points"].grad[vis, :2], dim=-1, keepdim=True)
+                den[vis] += 1
+            what = ("reference deform_network + reference extension (2 passes) + reference loss_utils (l1, ssim, depth l2)"
+                    + (" + reference compute_regulation" if reg is not None else "") + " + backward + torch stats + torch.optim.Adam") \
+                if lu is not None else "reference stack with plain L1/L2 (loss_utils.py not in oracle/_ref)"
+
+        def step_train():
+            for v in leaves:
+                v.grad = None
+            out = do_render()
+            full_loss(out).backward()
+            with torch.no_grad():
+                stats(out)
+            opt.step()
+        ms_train = timed(step_train, 10, 3)
+        train_it = {"ms": round(ms_train / 10, 4), "iterations": 10, "what": what}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.impl == "ours":
         # north_star: the reference's PyTorch HexPlane/deformation path on the box's host cores
@@ -528,6 +581,8 @@ def main_fine(a, rank, world, local, dev):
         out["impl"] = "reference"
     elif cpu:
         out["cpu_baseline"] = cpu
+    if train_it:
+        out["train_iteration"] = train_it
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

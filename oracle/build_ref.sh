@@ -26,7 +26,7 @@ DGR="$REF/submodules/depth-diff-gaussian-rasterization"
 mkdir -p "$OUT/diff_gaussian_rasterization" "$OUT/s3g_ref/scene" "$OUT/s3g_ref/utils"
 
 # --- python half (pure copies into the git-ignored install dir) -------------
-cp -f "$REF/scene/hexplane.py" "$REF/scene/deformation.py" "$REF/scene/grid.py" "$REF/scene/gaussian_model.py" "$OUT/s3g_ref/scene/"
+cp -f "$REF/scene/hexplane.py" "$REF/scene/deformation.py" "$REF/scene/grid.py" "$REF/scene/gaussian_model.py" "$REF/scene/regulation.py" "$OUT/s3g_ref/scene/"
 cp -f "$REF/utils/graphics_utils.py" "$REF/utils/sh_utils.py" "$REF/utils/loss_utils.py" "$REF/utils/general_utils.py" "$OUT/s3g_ref/utils/"
 cp -f "$REF/arguments/__init__.py" "$OUT/s3g_ref/arguments_init.py"
 cp -f "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"

@@ -168,3 +168,33 @@ def load_ref_gaussian_model_class():
         setattr(RefGaussianModel, m, cls_ns[m])
     # the extracted functions look their globals up in cls_ns (torch, nn, build_rotation, inverse_sigmoid)
     return RefGaussianModel
+
+
+def load_ref_compute_regulation():
+    """-> f(reference deform_network, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight): the UNMODIFIED
+    GaussianModel.compute_regulation + helpers (scene/gaussian_model.py:710-749) and compute_plane_smoothness
+    (scene/regulation.py:22-28), extracted with ast (the modules import matplotlib / open3d / simple_knn)."""
+    import ast
+    import types
+    import torch
+    base = os.path.join(REF_DIR, "s3g_ref", "scene")
+    ns = {"torch": torch}
+
+    def grab(path, names):
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    grab(os.path.join(base, "regulation.py"), {"compute_plane_smoothness"})
+    names = ("_plane_regulation", "_time_regulation", "_l1_regulation", "compute_regulation")
+    grab(os.path.join(base, "gaussian_model.py"), set(names))
+
+    def run(net, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight):
+        model = types.SimpleNamespace(_deformation=net)
+        for m in names[:3]:
+            setattr(model, m, types.MethodType(ns[m], model))
+        return ns["compute_regulation"](model, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight)
+    return run
+
+
+def regulation_available() -> bool:
+    return gaussian_model_available() and os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "scene", "regulation.py"))

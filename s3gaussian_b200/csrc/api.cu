@@ -12,35 +12,20 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/s3g_b200.h"
+#include "api_common.cuh"
 #include "binning.cuh"
 #include "common.cuh"
 #include "composite.cuh"
-#include "deform.cuh"
-#include "deform_tc.cuh"
 #include "preprocess.cuh"
 #include "radix_sort.cuh"
-#include "train_step.cuh"
 
 using namespace s3g;
 
 namespace {
 thread_local std::string g_last_error;
 
-int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
-    g_last_error = what;
-    if (e != cudaSuccess) {
-        g_last_error += ": ";
-        g_last_error += cudaGetErrorString(e);
-    }
-    return code;
-}
+inline int fail(int code, const char* what, cudaError_t e = cudaSuccess) { return s3g::api_fail(code, what, e); }
 
-#define S3G_CUDA(call, what)                                        \
-    do {                                                            \
-        cudaError_t e__ = (call);                                   \
-        if (e__ != cudaSuccess) return fail(S3G_ERR_CUDA, what, e__); \
-    } while (0)
 
 // debug mode: synchronise + check after every stage (CHECK_CUDA, auxiliary.h:166-173)
 #define S3G_STAGE(what)                                                            \
@@ -78,6 +63,16 @@ int tile_key_bits(uint32_t tiles) {
     return b < 1 ? 1 : b;
 }
 }  // namespace
+namespace s3g {
+int api_fail(int code, const char* what, cudaError_t e) {
+    g_last_error = what;
+    if (e != cudaSuccess) {
+        g_last_error += ": ";
+        g_last_error += cudaGetErrorString(e);
+    }
+    return code;
+}
+}  // namespace s3g
 
 extern "C" {
 
@@ -435,522 +430,6 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     }
     S3G_STAGE("preprocess_backward");
     S3G_MARK(1, nullptr);
-    return S3G_OK;
-}
-
-}  // extern "C"
-
-// ---------------------------------------------------------------------------
-// HexPlane + decoder
-// ---------------------------------------------------------------------------
-namespace {
-int to_dnet(const s3g_deform_net* n, DNet& d) {
-    if (!n) return fail(S3G_ERR_ARG, "deform: null net");
-    if (n->feat_dim != FD) return fail(S3G_ERR_UNSUPPORTED, "deform: output_coordinate_dim must be 32");
-    if (n->width != HWID) return fail(S3G_ERR_UNSUPPORTED, "deform: net_width must be 64");
-    if (!(n->num_levels == 1 || n->num_levels == 2 || n->num_levels == 3 || n->num_levels == 4 ||
-          n->num_levels == 8))
-        return fail(S3G_ERR_UNSUPPORTED, "deform: number of HexPlane levels must be 1, 2, 3, 4 or 8");
-    d.L = n->num_levels;
-    for (int l = 0; l < d.L; ++l) {
-        for (int c = 0; c < 4; ++c) {
-            d.reso[l][c] = n->reso[l][c];
-            if (d.reso[l][c] < 2) return fail(S3G_ERR_ARG, "deform: plane resolution < 2");
-        }
-        for (int k = 0; k < 6; ++k) {
-            d.planes[l][k] = n->planes[l][k];
-            if (!d.planes[l][k]) return fail(S3G_ERR_ARG, "deform: null plane");
-        }
-    }
-    for (int c = 0; c < 3; ++c) {
-        d.aabb0[c] = n->aabb[c];
-        d.inv_span2[c] = 2.0f / (n->aabb[3 + c] - n->aabb[c]);   // hexplane.py:19-20
-    }
-    if (!n->w_feat || !n->b_feat) return fail(S3G_ERR_ARG, "deform: null feature_out");
-    d.w_feat = n->w_feat; d.b_feat = n->b_feat;
-    d.pos = {n->w_pos1, n->b_pos1, n->w_pos2, n->b_pos2};
-    d.scl = {n->w_scl1, n->b_scl1, n->w_scl2, n->b_scl2};
-    d.rot = {n->w_rot1, n->b_rot1, n->w_rot2, n->b_rot2};
-    d.opa = {n->w_opa1, n->b_opa1, n->w_opa2, n->b_opa2};
-    d.shs = {n->w_shs1, n->b_shs1, n->w_shs2, n->b_shs2};
-    d.w_d0 = n->w_dino0; d.b_d0 = n->b_dino0; d.w_d2 = n->w_dino2; d.b_d2 = n->b_dino2;
-    d.w_d4 = n->w_dino4; d.b_d4 = n->b_dino4;
-    const Head2* hs[5] = {&d.pos, &d.scl, &d.rot, &d.opa, &d.shs};
-    for (const Head2* h : hs)
-        if (h->w1 && !(h->b1 && h->w2 && h->b2)) return fail(S3G_ERR_ARG, "deform: incomplete head");
-    if (d.w_d0 && !(d.b_d0 && d.w_d2 && d.b_d2 && d.w_d4 && d.b_d4))
-        return fail(S3G_ERR_ARG, "deform: incomplete dino head");
-    return S3G_OK;
-}
-// weight matrices in the order one tile consumes them (see WPipe)
-void build_wseq(const DNet& d, bool backward, WSeq& q) {
-    q.count = 0;
-    auto add = [&](const float* W, int N, int K) { q.W[q.count] = W; q.N[q.count] = (short)N; q.K[q.count] = (short)K; ++q.count; };
-    const int KF = FD * d.L;
-    add(d.w_feat, 64, KF);
-    const Head2* small[4] = {&d.pos, &d.scl, &d.rot, &d.opa};
-    for (const Head2* h : small)
-        if (h->w1) { add(h->w1, 64, 64); if (backward) add(h->w1, 64, 64); }
-    if (d.shs.w1) {
-        add(d.shs.w1, 64, 64); add(d.shs.w2, 48, 64);
-        if (backward) { add(d.shs.w2, 48, 64); add(d.shs.w1, 64, 64); }
-    }
-    if (d.w_d0) {
-        add(d.w_d0, 64, 64); add(d.w_d2, 64, 64);
-        if (backward) { add(d.w_d2, 64, 64); add(d.w_d0, 64, 64); }
-    }
-    if (backward) add(d.w_feat, 64, KF);
-}
-// prepared-weight table of the tcgen05 decoder
-void build_tc_table(const DNet& d, TcTable& t, TcPrepArgs* prep) {
-    int off = 0;
-    auto put = [&](int id, const float* W, int N, int K) {
-        if (!W) { t.off[id] = -1; t.npad[id] = 0; t.k[id] = 0; if (prep) { prep->W[id] = nullptr; prep->n[id] = 0; } return; }
-        const int np = (N + 15) & ~15;
-        t.off[id] = off; t.npad[id] = np; t.k[id] = K;
-        off += 2 * np * K;
-        if (prep) { prep->W[id] = W; prep->n[id] = N; }
-    };
-    put(TL_FEAT, d.w_feat, 64, FD * d.L);
-    put(TL_POS1, d.pos.w1, 64, 64); put(TL_POS2, d.pos.w1 ? d.pos.w2 : nullptr, 3, 64);
-    put(TL_SCL1, d.scl.w1, 64, 64); put(TL_SCL2, d.scl.w1 ? d.scl.w2 : nullptr, 3, 64);
-    put(TL_ROT1, d.rot.w1, 64, 64); put(TL_ROT2, d.rot.w1 ? d.rot.w2 : nullptr, 4, 64);
-    put(TL_OPA1, d.opa.w1, 64, 64); put(TL_OPA2, d.opa.w1 ? d.opa.w2 : nullptr, 1, 64);
-    put(TL_SHS1, d.shs.w1, 64, 64); put(TL_SHS2, d.shs.w1 ? d.shs.w2 : nullptr, 48, 64);
-    put(TL_D0, d.w_d0, 64, 64); put(TL_D2, d.w_d0 ? d.w_d2 : nullptr, 64, 64); put(TL_D4, d.w_d0 ? d.w_d4 : nullptr, 3, 64);
-    t.total = off;
-}
-int deform_grid(int ntiles) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int g = sms;      // one persistent CTA per SM (shared memory: weights double-buffered)
-    return ntiles < g ? ntiles : g;
-}
-}  // namespace
-
-extern "C" {
-
-int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
-                       const float* rotations, const float* opacity, const float* shs, float time,
-                       const float* campos, int sh_degree, float* means3D, float* scales_act,
-                       float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
-                       float* feat, float* features, void* workspace, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
-    if (P == 0) return S3G_OK;
-    DeformFwdArgs a;
-    int rc = to_dnet(net, a.net);
-    if (rc != S3G_OK) return rc;
-    if (!xyz || !scales || !rotations || !opacity || !shs || !campos)
-        return fail(S3G_ERR_ARG, "deform_forward: null input");
-    if (!means3D || !scales_act || !rot_act || !opacity_act || !colors || !features)
-        return fail(S3G_ERR_ARG, "deform_forward: null output");
-    if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_forward: sh_degree must be 0..3");
-    a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
-    a.campos = campos; a.time = time; a.sh_degree = sh_degree;
-    a.o_means = means3D; a.o_scales = scales_act; a.o_rot = rot_act; a.o_opacity = opacity_act;
-    a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat; a.features = features;
-    build_wseq(a.net, false, a.wseq);
-    {
-        SampleArgs sa;
-        sa.net = a.net; sa.P = P; sa.xyz = xyz; sa.time = time; sa.features = features;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int blocks = std::min((P + 7) / 8, sms * 12);
-        if (a.net.L == 4) hexplane_sample_kernel<4><<<blocks, 256, 0, stream>>>(sa);
-        else hexplane_sample_kernel<0><<<blocks, 256, 0, stream>>>(sa);
-        S3G_CUDA(cudaGetLastError(), "hexplane_sample launch");
-    }
-    if (a.net.L <= 4) {
-        // ---- decoder on the 5th-gen tensor cores (tcgen05 / TMEM) ------------------------------
-        if (!workspace) return fail(S3G_ERR_ARG, "deform_forward: null workspace");
-        DeformTcArgs t;
-        t.net = a.net; t.P = P; t.xyz = xyz; t.scales = scales; t.rot = rotations; t.opacity = opacity; t.shs = shs;
-        t.campos = campos; t.sh_degree = sh_degree;
-        t.o_means = means3D; t.o_scales = scales_act; t.o_rot = rot_act; t.o_opacity = opacity_act; t.o_colors = colors;
-        t.o_dx = dx; t.o_dshs = dshs; t.o_feat = feat; t.features = features;
-        TcPrepArgs pp;
-        build_tc_table(a.net, t.tab, &pp);
-        pp.tab = t.tab;
-        pp.dst = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-        t.wprep = pp.dst;
-        tc_prep_weights_kernel<<<dim3(8, TL_COUNT), 256, 0, stream>>>(pp);
-        S3G_CUDA(cudaGetLastError(), "tc_prep_weights launch");
-        const size_t smem = (size_t)(2 * TCM * 128 + 2 * 64 * 128) * sizeof(float);
-        S3G_CUDA(cudaFuncSetAttribute(deform_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform tc smem attr");
-        const int ntiles = (P + TCM - 1) / TCM;
-        deform_forward_tc_kernel<<<deform_grid(ntiles), TCM, smem, stream>>>(t);
-    } else {
-        const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
-        const int ntiles = (P + DT - 1) / DT;
-        S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
-        deform_forward_kernel<0><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
-    }
-    S3G_CUDA(cudaGetLastError(), "deform_forward launch");
-    return S3G_OK;
-}
-
-
-namespace {
-// layout of one CTA's partial-gradient buffer
-int make_offsets(const DNet& d, GradOff& o) {
-    int t = 0;
-    auto take = [&](int n) { int r = t; t += (n + 3) & ~3; return r; };
-    auto head = [&](const Head2& h, int k, int (&dst)[4]) {
-        if (h.w1) { dst[0] = take(64 * 64); dst[1] = take(64); dst[2] = take(k * 64); dst[3] = take(k); }
-        else { dst[0] = dst[1] = dst[2] = dst[3] = -1; }
-    };
-    o.w_feat = take(64 * FD * d.L); o.b_feat = take(64);
-    head(d.pos, 3, o.pos); head(d.scl, 3, o.scl); head(d.rot, 4, o.rot); head(d.opa, 1, o.opa); head(d.shs, 48, o.shs);
-    if (d.w_d0) { o.d0w = take(4096); o.d0b = take(64); o.d2w = take(4096); o.d2b = take(64); o.d4w = take(192); o.d4b = take(3); }
-    else { o.d0w = o.d0b = o.d2w = o.d2b = o.d4w = o.d4b = -1; }
-    o.total = t;
-    return t;
-}
-int bwd_grid(int ntiles) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return ntiles < sms ? ntiles : sms;
-}
-constexpr int kMaxBwdGrid = 256;
-}  // namespace
-
-size_t s3g_deform_forward_workspace_bytes(const s3g_deform_net* net) {
-    DNet d;
-    if (to_dnet(net, d) != S3G_OK) return 0;
-    TcTable t;
-    build_tc_table(d, t, nullptr);
-    return (size_t)t.total * sizeof(float) + 512;
-}
-
-size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
-    DNet d;
-    if (to_dnet(net, d) != S3G_OK) return 0;
-    GradOff o;
-    make_offsets(d, o);
-    // per-CTA partial Linear gradients + dL/d(features) [P][32L]
-    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float);
-}
-
-int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
-                        const float* rotations, const float* opacity, const float* shs, float time,
-                        const float* campos, int sh_degree, const float* features,
-                        const float* g_means3D, const float* g_scales_act, const float* g_rot_act, const float* g_opacity_act,
-                        const float* g_colors, const float* g_dx, const float* g_dshs, const float* g_feat,
-                        float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
-                        const s3g_deform_net_grads* grads, void* workspace, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (P < 0) return fail(S3G_ERR_ARG, "deform_backward: P < 0");
-    DeformBwdArgs a;
-    int rc = to_dnet(net, a.net);
-    if (rc != S3G_OK) return rc;
-    if (!grads || !workspace) return fail(S3G_ERR_ARG, "deform_backward: null grads/workspace");
-    if (P > 0 && (!xyz || !scales || !rotations || !opacity || !shs || !campos || !features))
-        return fail(S3G_ERR_ARG, "deform_backward: null input");
-    if (P > 0 && (!d_xyz || !d_scales || !d_rotations || !d_opacity || !d_shs))
-        return fail(S3G_ERR_ARG, "deform_backward: null output");
-    if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_backward: sh_degree must be 0..3");
-    const DNet& d = a.net;
-    a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
-    a.campos = campos; a.time = time; a.sh_degree = sh_degree;
-    a.g_means = g_means3D; a.g_scales = g_scales_act; a.g_rot = g_rot_act; a.g_opacity = g_opacity_act;
-    a.g_colors = g_colors; a.g_dx = g_dx; a.g_dshs = g_dshs; a.g_feat = g_feat;
-    a.d_xyz = d_xyz; a.d_scales = d_scales; a.d_rot = d_rotations; a.d_opacity = d_opacity; a.d_shs = d_shs;
-    for (int l = 0; l < d.L; ++l)
-        for (int k = 0; k < 6; ++k) {
-            a.gplanes[l][k] = grads->planes[l][k];
-            if (!a.gplanes[l][k]) return fail(S3G_ERR_ARG, "deform_backward: null plane gradient");
-        }
-    make_offsets(d, a.off);
-    build_wseq(d, true, a.wseq);
-    a.partial = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    a.features = features;
-    a.dfeatures = a.partial + (size_t)kMaxBwdGrid * a.off.total;
-    const int ntiles = (P + DT - 1) / DT;
-    int grid = bwd_grid(ntiles);
-    if (grid > kMaxBwdGrid) grid = kMaxBwdGrid;
-    // destination table of the reduction
-    ReduceArgs r;
-    r.nseg = 0; r.partial = a.partial; r.stride = a.off.total; r.nparts = grid > 0 ? grid : 0;
-    auto seg = [&](float* dst, int off, int count) -> bool {
-        if (off < 0) return true;
-        if (!dst) return false;
-        r.seg[r.nseg++] = ReduceSeg{dst, off, count};
-        return true;
-    };
-    bool ok = seg(grads->w_feat, a.off.w_feat, 64 * FD * d.L) && seg(grads->b_feat, a.off.b_feat, 64);
-    auto hseg = [&](const int (&o)[4], float* w1, float* b1, float* w2, float* b2, int k) {
-        return seg(w1, o[0], 4096) && seg(b1, o[1], 64) && seg(w2, o[2], k * 64) && seg(b2, o[3], k);
-    };
-    ok = ok && hseg(a.off.pos, grads->w_pos1, grads->b_pos1, grads->w_pos2, grads->b_pos2, 3);
-    ok = ok && hseg(a.off.scl, grads->w_scl1, grads->b_scl1, grads->w_scl2, grads->b_scl2, 3);
-    ok = ok && hseg(a.off.rot, grads->w_rot1, grads->b_rot1, grads->w_rot2, grads->b_rot2, 4);
-    ok = ok && hseg(a.off.opa, grads->w_opa1, grads->b_opa1, grads->w_opa2, grads->b_opa2, 1);
-    ok = ok && hseg(a.off.shs, grads->w_shs1, grads->b_shs1, grads->w_shs2, grads->b_shs2, 48);
-    ok = ok && seg(grads->w_dino0, a.off.d0w, 4096) && seg(grads->b_dino0, a.off.d0b, 64) &&
-         seg(grads->w_dino2, a.off.d2w, 4096) && seg(grads->b_dino2, a.off.d2b, 64) &&
-         seg(grads->w_dino4, a.off.d4w, 192) && seg(grads->b_dino4, a.off.d4b, 3);
-    if (!ok) return fail(S3G_ERR_ARG, "deform_backward: null Linear gradient for an enabled layer");
-    if (P > 0) {
-        const size_t smem = DeformBwdSmem::floats(d.L) * sizeof(float);
-        if (smem > 227 * 1024) return fail(S3G_ERR_UNSUPPORTED, "deform_backward: too many levels for shared memory");
-        if (d.L == 4) {
-            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
-            deform_backward_kernel<4><<<grid, DTHREADS, smem, stream>>>(a);
-        } else {
-            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
-            deform_backward_kernel<0><<<grid, DTHREADS, smem, stream>>>(a);
-        }
-        S3G_CUDA(cudaGetLastError(), "deform_backward launch");
-        ScatterArgs sc;
-        sc.net = a.net; sc.P = P; sc.xyz = xyz; sc.time = time; sc.dfeatures = a.dfeatures; sc.d_xyz = d_xyz;
-        for (int l = 0; l < S3G_MAX_LEVELS; ++l)
-            for (int k = 0; k < 6; ++k) sc.gplanes[l][k] = l < d.L ? a.gplanes[l][k] : nullptr;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int blocks = std::min((P + 7) / 8, sms * 8);
-        if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
-        else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
-        S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
-    }
-    {
-        int maxc = 1;
-        for (int i = 0; i < r.nseg; ++i) maxc = std::max(maxc, r.seg[i].count);
-        deform_reduce_kernel<<<dim3((maxc + 255) / 256, r.nseg), 256, 0, stream>>>(r);
-    }
-    S3G_CUDA(cudaGetLastError(), "deform_reduce launch");
-    return S3G_OK;
-}
-
-// ---- training-step kernels (train_step.cuh) --------------------------------------------------
-int s3g_adam_step(int n, const s3g_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (n < 0 || (n > 0 && !tensors)) return fail(S3G_ERR_ARG, "adam_step: bad tensor table");
-    AdamArgs a;
-    a.w1 = (float)(1.0 - beta1);
-    a.beta2 = (float)beta2;
-    a.omb2 = (float)(1.0 - beta2);
-    a.eps = (float)eps;
-    int i = 0;
-    while (i < n) {
-        a.count = 0;
-        int blocks = 0;
-        for (; i < n && a.count < ADAM_MAX_TENSORS; ++i) {
-            const s3g_adam_tensor& t = tensors[i];
-            if (t.numel == 0) continue;
-            if (t.numel < 0 || !t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq || t.step < 1)
-                return fail(S3G_ERR_ARG, "adam_step: null pointer, negative numel or step < 1");
-            const long long nb = (t.numel + ADAM_CHUNK - 1) / ADAM_CHUNK;
-            if (nb + blocks > 0x7fffffffLL) return fail(S3G_ERR_ARG, "adam_step: tensor too large");
-            AdamTensor& d = a.t[a.count];
-            d.p = t.param; d.g = t.grad; d.m = t.exp_avg; d.v = t.exp_avg_sq; d.n = t.numel;
-            const double bc1 = 1.0 - std::pow(beta1, (double)t.step);
-            const double bc2 = 1.0 - std::pow(beta2, (double)t.step);
-            d.step_size = (float)(t.lr / bc1);
-            d.bc2_sqrt = (float)std::sqrt(bc2);
-            a.block_start[a.count] = blocks;
-            blocks += (int)nb;
-            ++a.count;
-        }
-        a.block_start[a.count] = blocks;
-        if (blocks > 0) {
-            adam_multi_tensor_kernel<<<blocks, ADAM_THREADS, 0, stream>>>(a);
-            S3G_CUDA(cudaGetLastError(), "adam_step launch");
-        }
-    }
-    return S3G_OK;
-}
-
-int s3g_densify_stats(int P, const float* viewspace_grad, const int* radii, float* xyz_gradient_accum,
-                      float* denom, float* max_radii2D, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (P < 0) return fail(S3G_ERR_ARG, "densify_stats: P < 0");
-    if (P == 0) return S3G_OK;
-    if (!viewspace_grad || !radii || !xyz_gradient_accum || !denom || !max_radii2D)
-        return fail(S3G_ERR_ARG, "densify_stats: null pointer");
-    densify_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, viewspace_grad, radii, xyz_gradient_accum, denom, max_radii2D);
-    S3G_CUDA(cudaGetLastError(), "densify_stats launch");
-    return S3G_OK;
-}
-
-namespace {
-constexpr int kDepthBlocks = 592;    // 4 per SM
-struct LossPlan {
-    size_t map_floats, img_blocks;
-    dim3 grid;
-};
-LossPlan loss_plan(int B, int C, int H, int W) {
-    LossPlan p;
-    p.map_floats = (size_t)B * C * H * W;
-    p.grid = dim3((W + LOSS_T - 1) / LOSS_T, (H + LOSS_T - 1) / LOSS_T, B * C);
-    p.img_blocks = (size_t)p.grid.x * p.grid.y * p.grid.z;
-    return p;
-}
-}  // namespace
-
-size_t s3g_image_loss_workspace_bytes(int B, int C, int H, int W) {
-    if (B <= 0 || C < 0 || H <= 0 || W <= 0) return 0;
-    const LossPlan p = loss_plan(B, C, H, W);
-    return 256 + sizeof(float) * (3 * p.map_floats + 2 * p.img_blocks + 2 * kDepthBlocks);
-}
-
-namespace {
-struct LossBufs { float *m0, *m1, *m2, *part_img, *part_dep; };
-LossBufs loss_bufs(const LossPlan& p, const void* workspace) {
-    LossBufs b;
-    float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    b.m0 = ws; b.m1 = b.m0 + p.map_floats; b.m2 = b.m1 + p.map_floats;
-    b.part_img = b.m2 + p.map_floats; b.part_dep = b.part_img + 2 * p.img_blocks;
-    return b;
-}
-LossWin loss_window() {
-    // gaussian(11, 1.5) of loss_utils.py:56-58: float32 exp values normalised by their float32 sum
-    LossWin win;
-    float g[11], s = 0.f;
-    for (int x = 0; x < 11; ++x) g[x] = (float)std::exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5));
-    for (int x = 0; x < 11; ++x) s += g[x];
-    for (int x = 0; x < 11; ++x) win.w[x] = g[x] / s;
-    return win;
-}
-int loss_check(int B, int C, int H, int W, const void* image, const void* gt, const void* depth, const void* gt_depth) {
-    if (B <= 0 || C < 0 || H <= 0 || W <= 0) return fail(S3G_ERR_ARG, "image_loss: empty image");
-    if ((long long)B * C > 65535) return fail(S3G_ERR_ARG, "image_loss: too many image planes");
-    if (C > 0 && (!image || !gt)) return fail(S3G_ERR_ARG, "image_loss: null image pointer");
-    if (C == 0 && !depth) return fail(S3G_ERR_ARG, "image_loss: neither image nor depth");
-    if ((depth == nullptr) != (gt_depth == nullptr)) return fail(S3G_ERR_ARG, "image_loss: depth and gt_depth go together");
-    return S3G_OK;
-}
-}  // namespace
-
-int s3g_image_loss_forward(int B, int C, int H, int W, const float* image, const float* gt_image, const float* depth,
-                           const float* gt_depth, float max_depth, double* sums, void* workspace, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (int rc = loss_check(B, C, H, W, image, gt_image, depth, gt_depth)) return rc;
-    if (!sums || !workspace) return fail(S3G_ERR_ARG, "image_loss_forward: null sums/workspace");
-    const LossPlan p = loss_plan(B, C, H, W);
-    const LossBufs b = loss_bufs(p, workspace);
-    if (C > 0) {
-        loss_stats_kernel<<<p.grid, LOSS_THREADS, 0, stream>>>(H, W, image, gt_image, loss_window(), b.m0, b.m1, b.m2, b.part_img);
-        S3G_CUDA(cudaGetLastError(), "loss_stats launch");
-    }
-    int ndep = 0;
-    if (depth) {
-        ndep = kDepthBlocks;
-        loss_depth_stats_kernel<<<kDepthBlocks, LOSS_THREADS, 0, stream>>>((size_t)B * H * W, depth, gt_depth, max_depth, b.part_dep);
-        S3G_CUDA(cudaGetLastError(), "loss_depth_stats launch");
-    }
-    loss_reduce_kernel<<<1, 256, 0, stream>>>((int)p.img_blocks, b.part_img, ndep, b.part_dep, sums);
-    S3G_CUDA(cudaGetLastError(), "loss_reduce launch");
-    return S3G_OK;
-}
-
-int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, const float* gt_image, const float* depth,
-                            const float* gt_depth, float max_depth, const float* weights, const double* sums,
-                            const void* workspace, float* g_image, float* g_depth, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (int rc = loss_check(B, C, H, W, image, gt_image, depth, gt_depth)) return rc;
-    if (!weights || !sums || !workspace || (C > 0 && !g_image) || (depth && !g_depth))
-        return fail(S3G_ERR_ARG, "image_loss_backward: null pointer");
-    const LossPlan p = loss_plan(B, C, H, W);
-    const LossBufs b = loss_bufs(p, workspace);
-    if (C > 0) {
-        loss_grad_kernel<<<p.grid, LOSS_THREADS, 0, stream>>>(H, W, image, gt_image, loss_window(), b.m0, b.m1, b.m2, weights,
-                                                             1.0f / (float)p.map_floats, g_image);
-        S3G_CUDA(cudaGetLastError(), "loss_grad launch");
-    }
-    if (depth) {
-        const size_t nd = (size_t)B * H * W;
-        loss_depth_grad_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, stream>>>(nd, depth, gt_depth, max_depth, weights, sums, g_depth);
-        S3G_CUDA(cudaGetLastError(), "loss_depth_grad launch");
-    }
-    return S3G_OK;
-}
-
-// ---- HexPlane regularisers -------------------------------------------------------------------
-namespace {
-int reg_table(int n, const s3g_plane_desc* planes, bool need_grad, RegArgs& a) {
-    if (n <= 0 || n > REG_MAX_PLANES || !planes) return fail(S3G_ERR_ARG, "plane_reg: 1..48 planes expected");
-    int blocks = 0;
-    a.count = n;
-    for (int i = 0; i < n; ++i) {
-        const s3g_plane_desc& d = planes[i];
-        if (!d.plane || (need_grad && !d.grad)) return fail(S3G_ERR_ARG, "plane_reg: null plane / grad pointer");
-        if (d.H < 3 || d.W < 1 || d.C < 4 || d.C % 4) return fail(S3G_ERR_ARG, "plane_reg: need H >= 3, W >= 1, C % 4 == 0");
-        RegPlane& p = a.p[i];
-        p.t = d.plane; p.g = d.grad; p.H = d.H; p.W = d.W; p.C = d.C;
-        p.k_smooth = (float)((double)d.w_smooth / ((double)d.C * (d.H - 2) * d.W));
-        p.k_l1 = (float)((double)d.w_l1 / ((double)d.C * d.H * d.W));
-        const long long n4 = (long long)d.H * d.W * d.C / 4;
-        a.block_start[i] = blocks;
-        const long long nb = (n4 + REG_CHUNK4 - 1) / REG_CHUNK4;
-        if (blocks + nb > 0x7fffffffLL) return fail(S3G_ERR_ARG, "plane_reg: planes too large");
-        blocks += (int)nb;
-    }
-    a.block_start[n] = blocks;
-    return blocks;
-}
-}  // namespace
-
-size_t s3g_plane_reg_workspace_bytes(int n, const s3g_plane_desc* planes) {
-    RegArgs a;
-    const int blocks = reg_table(n, planes, false, a);
-    return blocks < 0 ? 0 : 256 + sizeof(double) * (size_t)blocks;
-}
-
-int s3g_plane_reg_forward(int n, const s3g_plane_desc* planes, double* total, void* workspace, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    RegArgs a;
-    const int blocks = reg_table(n, planes, false, a);
-    if (blocks < 0) return blocks;
-    if (!total || !workspace) return fail(S3G_ERR_ARG, "plane_reg_forward: null total/workspace");
-    double* partial = reinterpret_cast<double*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    plane_reg_forward_kernel<<<blocks, REG_THREADS, 0, stream>>>(a, partial);
-    S3G_CUDA(cudaGetLastError(), "plane_reg_forward launch");
-    plane_reg_reduce_kernel<<<1, 256, 0, stream>>>(blocks, partial, total);
-    S3G_CUDA(cudaGetLastError(), "plane_reg_reduce launch");
-    return S3G_OK;
-}
-
-int s3g_plane_reg_backward(int n, const s3g_plane_desc* planes, const float* gscale, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    RegArgs a;
-    const int blocks = reg_table(n, planes, true, a);
-    if (blocks < 0) return blocks;
-    if (!gscale) return fail(S3G_ERR_ARG, "plane_reg_backward: null gscale");
-    plane_reg_backward_kernel<<<blocks, REG_THREADS, 0, stream>>>(a, gscale);
-    S3G_CUDA(cudaGetLastError(), "plane_reg_backward launch");
-    return S3G_OK;
-}
-
-// ---- densify / prune row gather ----------------------------------------------------------------
-int s3g_gather_rows(int n, const s3g_row_tensor* tensors, int64_t n_out, int64_t n_kept, const int64_t* src_index,
-                    void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (n <= 0 || n > ROWS_MAX_TENSORS || !tensors) return fail(S3G_ERR_ARG, "gather_rows: 1..32 tensors expected");
-    if (n_out < 0 || n_kept < 0 || n_kept > n_out) return fail(S3G_ERR_ARG, "gather_rows: need 0 <= n_kept <= n_out");
-    if (n_out == 0) return S3G_OK;
-    if (!src_index) return fail(S3G_ERR_ARG, "gather_rows: null src_index");
-    RowArgs a;
-    a.count = n; a.n_out = n_out; a.n_kept = n_kept;
-    a.src_index = reinterpret_cast<const long long*>(src_index);
-    long long most = 0;
-    for (int i = 0; i < n; ++i) {
-        const s3g_row_tensor& t = tensors[i];
-        if (!t.src || !t.dst || t.row_floats <= 0) return fail(S3G_ERR_ARG, "gather_rows: null pointer or row_floats <= 0");
-        a.t[i] = RowTensor{t.src, t.dst, t.row_floats, t.zero_new};
-        most = std::max(most, (long long)n_out * t.row_floats);
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long want = (most + 255) / 256;
-    const int gx = (int)std::min<long long>(want, (long long)sms * 8);
-    gather_rows_kernel<<<dim3(gx, n), 256, 0, stream>>>(a);
-    S3G_CUDA(cudaGetLastError(), "gather_rows launch");
     return S3G_OK;
 }
 

@@ -38,6 +38,42 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+constexpr uint32_t LB_FLAG_AGG = 1u << 30;
+constexpr uint32_t LB_FLAG_INCL = 2u << 30;
+constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1u;
+constexpr int LB_WINDOW = 8;
+
+// block-wide exclusive scan of one value per thread (256 threads)
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/,
+                                                        uint32_t* total = nullptr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_THREADS / 32; ++w) {
+        uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        tot += c;
+    }
+    if (total) *total = tot;
+    __syncthreads();
+    return wbase + inc - v;
+}
+
+// The sort kernels and their host driver are compiled in their own translation unit (radix_sort.cu,
+// which defines S3G_RADIX_SORT_IMPL); everyone else sees the declaration only.
+cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_tmp,
+                             uint32_t* vals_tmp, uint32_t* keys_final, uint32_t* vals_final, int begin_bit,
+                             int end_bit, const SortTemp& st, cudaStream_t stream);
+
+#ifdef S3G_RADIX_SORT_IMPL
 // ---- histogram of every digit of every pass in one read of the keys -------
 // grid: any (grid-stride by tiles of 256*16); hist: [npass][RADIX], pre-zeroed.
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -67,34 +103,6 @@ sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int begin_b
     }
 }
 
-constexpr uint32_t LB_FLAG_AGG = 1u << 30;
-constexpr uint32_t LB_FLAG_INCL = 2u << 30;
-constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1u;
-constexpr int LB_WINDOW = 8;
-
-// block-wide exclusive scan of one value per thread (256 threads)
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/,
-                                                        uint32_t* total = nullptr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t wbase = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_THREADS / 32; ++w) {
-        uint32_t c = s_warp[w];
-        if (w < warp) wbase += c;
-        tot += c;
-    }
-    if (total) *total = tot;
-    __syncthreads();
-    return wbase + inc - v;
-}
 
 // ---- one digit pass --------------------------------------------------------
 // grid: exactly ceil(n / SORT_TILE) blocks.  status: [nblk][RADIX] zeroed.
@@ -146,6 +154,14 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[i] = old + __popc(peers & lt);
         __syncwarp();
+    }
+    // the values are only needed for the scatter; fetching them here (not there) keeps the global round
+    // trip off the critical path behind the look-back
+    uint32_t v_in[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        uint32_t idx = base + i * 32 + lane;
+        v_in[i] = idx < n ? vals_in[idx] : 0u;
     }
     __syncthreads();
     // digit tid: exclusive prefix over warps, block count
@@ -200,9 +216,8 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     for (int i = 0; i < SORT_ITEMS; ++i) {
         uint32_t d = (k[i] >> shift) & mask;
         uint32_t lp = s_dstart[d] + s_wc[warp][d] + rank[i];
-        uint32_t idx = base + i * 32 + lane;
         s_keys[lp] = k[i];
-        s_vals[lp] = idx < n ? vals_in[idx] : 0u;
+        s_vals[lp] = v_in[i];
     }
     __syncthreads();
 #pragma unroll
@@ -223,7 +238,7 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 // writes to (keys_final,vals_final) (keys_final may be NULL = don't care).
 // `st` must have been carved for >= n items.  Returns the cudaError of the
 // launches.
-inline cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
+cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
                                     uint32_t* keys_tmp, uint32_t* vals_tmp, uint32_t* keys_final,
                                     uint32_t* vals_final, int begin_bit, int end_bit,
                                     const SortTemp& st, cudaStream_t stream) {
@@ -262,7 +277,9 @@ inline cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* val
     }
     return cudaGetLastError();
 }
+#endif  // S3G_RADIX_SORT_IMPL
 
+#ifndef S3G_RADIX_SORT_IMPL   // the scan below belongs to the including translation unit (api.cu)
 // ---- chained exclusive scan of tiles_touched[order[k]] ---------------------
 // Replaces cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:278), but over the
 // depth-sorted order and exclusive.  misc[0] = ticket (zeroed), total written to
@@ -323,5 +340,7 @@ scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict
         run += v[i];
     }
 }
+
+#endif
 
 }  // namespace s3g

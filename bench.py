@@ -262,8 +262,17 @@ def main():
         # per visible Gaussian the 40-byte gradient record it produces
         alg = R * 44 + W * H * 24 + V * 40
         ach = alg / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        # dram__bytes_read+write of one launch of this kernel from the committed ncu --set full capture of the same
+        # workload (profiles/ncu_traffic.json); only quoted when the workload is the one that was profiled
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if (P, W, H, a.mode) == (2_000_000, 1920, 1280, "sh"):
+                traffic = int(tj["kernels"]["render_backward_kernel"]["dram_bytes"])
+        except Exception:
+            pass
         roofline = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": round(ach, 2), "peak": hbm,
-                    "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": None,
+                    "unit": "GB/s", "frac": round(ach / hbm, 4), "traffic": traffic,
                     "algorithmic_bytes": int(alg), "kernel_ms": round(kern_ms, 4), "peak_source": peak_src,
                     "note": "issue-bound all-lanes composite; see DESIGN.md (roofline) for why the HBM fraction is low"}
         sh = a.mode == "sh"

@@ -330,6 +330,15 @@ typedef struct s3g_row_tensor {
 int s3g_gather_rows(int n, const s3g_row_tensor* tensors, int64_t n_out, int64_t n_kept, const int64_t* src_index,
                     void* stream);
 
+/* ---- initialisation --------------------------------------------------------
+ * s3g_knn_mean_dist2  <- simple_knn._C.distCUDA2 (SimpleKNN::knn)   submodules/simple-knn/simple_knn.cu:185-221,
+ *                        called at scene/gaussian_model.py:153 to initialise the scales
+ * mean_dist2[i] = mean of the squared distances from points[i] to its 3 nearest OTHER points
+ * (exact; coincident points count with distance 0).  points: f32[P,3]; workspace:
+ * s3g_knn_workspace_bytes(P) bytes.  No host synchronisation. */
+size_t s3g_knn_workspace_bytes(int P);
+int s3g_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

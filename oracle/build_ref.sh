@@ -12,6 +12,7 @@
 # rasterizer_impl.h's std::uintptr_t; SURVEY.md header table).
 #
 #   oracle/_ref/diff_gaussian_rasterization/{__init__.py,_C*.so}   reference CUDA rasterizer, sm_100
+#   oracle/_ref/simple_knn/_C*.so                                  reference simple-knn (distCUDA2), sm_100
 #   oracle/_ref/s3g_ref/scene/{hexplane,deformation,grid}.py       reference HexPlane + decoder (PyTorch)
 #   oracle/_ref/s3g_ref/scene/gaussian_model.py                    densify / prune methods (extracted with ast by the tests)
 #   oracle/_ref/s3g_ref/utils/{graphics_utils,sh_utils,loss_utils,general_utils}.py
@@ -30,6 +31,20 @@ cp -f "$REF/scene/hexplane.py" "$REF/scene/deformation.py" "$REF/scene/grid.py" 
 cp -f "$REF/utils/graphics_utils.py" "$REF/utils/sh_utils.py" "$REF/utils/loss_utils.py" "$REF/utils/general_utils.py" "$OUT/s3g_ref/utils/"
 cp -f "$REF/arguments/__init__.py" "$OUT/s3g_ref/arguments_init.py"
 cp -f "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"
+
+# --- simple-knn (distCUDA2): reference initialiser of the scales, checker for csrc/knn.cuh -------------
+if ! ls "$OUT"/simple_knn/_C*.so >/dev/null 2>&1 || [ -n "${FORCE:-}" ]; then
+  KTMP="$(mktemp -d /tmp/sknn_build.XXXXXX)"
+  cp -r "$REF/submodules/simple-knn/." "$KTMP/"
+  chmod -R u+w "$KTMP"
+  # only deviation from "as is": <cfloat>/<cstdint> forced in (FLT_MAX, gcc 13)
+  ( cd "$KTMP" && NVCC_PREPEND_FLAGS="-include cfloat -include cstdint" TORCH_CUDA_ARCH_LIST="10.0" MAX_JOBS=8 \
+      python setup.py build_ext --inplace >"$KTMP/build.log" 2>&1 ) || { tail -40 "$KTMP/build.log"; exit 1; }
+  mkdir -p "$OUT/simple_knn"
+  cp "$KTMP"/simple_knn/_C*.so "$OUT/simple_knn/"
+  rm -rf "$KTMP"
+  echo "build_ref: simple_knn ok"
+fi
 
 # --- CUDA half ----------------------------------------------------------------
 if ls "$OUT"/diff_gaussian_rasterization/_C*.so >/dev/null 2>&1 && [ -z "${FORCE:-}" ]; then

@@ -17,12 +17,13 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libs3g_b200.so")
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
+OBJDIR = os.path.join(LIBDIR, "obj")
 
 
 def sources() -> list[str]:
@@ -42,23 +43,40 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
+def _compile_one(nvcc: str, src: str, obj: str, verbose: bool) -> str:
+    cmd = [nvcc, *COMPILE_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    log = ""
+    for attempt in (1, 2):      # cicc 12.9 has crashed on this code base; the crash moves with tiny edits - retry once
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = r.stdout + r.stderr
+        if r.returncode == 0:
+            return log
+    raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{log}")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One `nvcc -c` per translation unit (in parallel), then one link step."""
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libs3g_b200.so (there is no CPU fallback)")
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    srcs = sources()
+    objs = [os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        logs = list(ex.map(lambda so: _compile_one(nvcc, so[0], so[1], verbose), zip(srcs, objs)))
+    tmp = LIB + ".tmp"
+    r = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)
     if verbose:
-        print(r.stderr)
+        print("\n".join(logs))
     return LIB
 
 

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "composite.cuh"
 #include "preprocess.cuh"
+#define S3G_SCAN_IMPL
 #include "radix_sort.cuh"
 
 using namespace s3g;

@@ -279,7 +279,7 @@ cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
 }
 #endif  // S3G_RADIX_SORT_IMPL
 
-#ifndef S3G_RADIX_SORT_IMPL   // the scan below belongs to the including translation unit (api.cu)
+#ifdef S3G_SCAN_IMPL   // the scan below is compiled by api.cu only
 // ---- chained exclusive scan of tiles_touched[order[k]] ---------------------
 // Replaces cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:278), but over the
 // depth-sorted order and exclusive.  misc[0] = ticket (zeroed), total written to

@@ -19,8 +19,8 @@ Row order after every operation, Adam moments of kept / new rows, the random sam
 ``densify_and_split`` (same ``torch.normal`` call, so the same values for the same generator state)
 match the reference bit for bit (tests/test_gpu_train.py runs the reference's own methods side by side).
 
-Out of scope here: ``create_from_pcd`` (needs simple-knn's distCUDA2), .ply / checkpoint
-I/O.  CUDA only; no CPU path.
+``create_from_pcd`` uses our distCUDA2 (simple_knn.py, csrc/knn.cuh); ``save_ply`` / ``load_ply`` keep the
+reference's attribute layout (io_ply.py).  CUDA only; no CPU path.
 """
 from __future__ import annotations
 
@@ -117,9 +117,62 @@ class GaussianModel:
         self._deformation_table = torch.ones(P, dtype=torch.bool, device=dev)
         return self
 
-    def create_from_pcd(self, *a, **k):
-        raise NotImplementedError("create_from_pcd needs simple-knn's distCUDA2 (SURVEY 8f f-4); "
-                                  "initialise the tensors and call create_from_tensors")
+    def create_from_pcd(self, pcd, spatial_lr_scale: float):
+        """gaussian_model.py:141-169: positions and colours from a point cloud (anything with ``.points`` and
+        ``.colors`` [P,3] arrays, colours in [0,1]); isotropic scales from the mean squared distance to the three
+        nearest neighbours (our distCUDA2), identity rotations, opacity 0.1."""
+        import numpy as np
+        from .simple_knn import distCUDA2
+        dev = torch.device("cuda")
+        xyz = torch.tensor(np.asarray(pcd.points)).float().to(dev)
+        colour = (torch.tensor(np.asarray(pcd.colors)).float().to(dev) - 0.5) / 0.28209479177387814   # RGB2SH, sh_utils.py:114
+        P, K = xyz.shape[0], (self.max_sh_degree + 1) ** 2
+        features = torch.zeros((P, 3, K), device=dev)
+        features[:, :3, 0] = colour
+        dist2 = torch.clamp_min(distCUDA2(xyz), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+        rots = torch.zeros((P, 4), device=dev)
+        rots[:, 0] = 1
+        opacities = inverse_sigmoid(0.1 * torch.ones((P, 1), dtype=torch.float, device=dev))
+        return self.create_from_tensors(xyz, features[:, :, 0:1].transpose(1, 2), features[:, :, 1:].transpose(1, 2),
+                                        scales, rots, opacities, spatial_lr_scale)
+
+    # ---- .ply / deformation checkpoints (gaussian_model.py:241-275,355-395) ------------------------
+    def save_ply(self, path):
+        from .io_ply import write_gaussian_ply
+        write_gaussian_ply(path, self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling,
+                           self._rotation)
+
+    def load_ply(self, path, device="cuda"):
+        from .io_ply import read_gaussian_ply
+        d = read_gaussian_ply(path, self.max_sh_degree)
+        dev = torch.device(device)
+        self.create_from_tensors(d["xyz"].to(dev), d["features_dc"].to(dev), d["features_rest"].to(dev),
+                                 d["scaling"].to(dev), d["rotation"].to(dev), d["opacity"].to(dev),
+                                 self.spatial_lr_scale or 1.0)
+        self.active_sh_degree = self.max_sh_degree
+        return self
+
+    def save_deformation(self, path):
+        import os
+        os.makedirs(path, exist_ok=True)
+        torch.save(self._deformation.state_dict(), os.path.join(path, "deformation.pth"))
+        torch.save(self._deformation_table, os.path.join(path, "deformation_table.pth"))
+        torch.save(self._deformation_accum, os.path.join(path, "deformation_accum.pth"))
+
+    def load_model(self, path):
+        import os
+        dev = self._xyz.device if self._xyz.numel() else torch.device("cuda")
+        self._deformation.load_state_dict(torch.load(os.path.join(path, "deformation.pth"), map_location=dev))
+        self._deformation = self._deformation.to(dev)
+        P = self._xyz.shape[0]
+        self._deformation_table = torch.ones(P, dtype=torch.bool, device=dev)
+        self._deformation_accum = torch.zeros((P, 3), device=dev)
+        for name, attr in (("deformation_table.pth", "_deformation_table"), ("deformation_accum.pth", "_deformation_accum")):
+            f = os.path.join(path, name)
+            if os.path.exists(f):
+                setattr(self, attr, torch.load(f, map_location=dev))
+        self.max_radii2D = torch.zeros(P, device=dev)
 
     # ---- the accessors render() and the loop read (gaussian_model.py:113-140) --------------------
     @property

@@ -198,3 +198,21 @@ def load_ref_compute_regulation():
 
 def regulation_available() -> bool:
     return gaussian_model_available() and os.path.isfile(os.path.join(REF_DIR, "s3g_ref", "scene", "regulation.py"))
+
+
+# ---- the reference's simple-knn extension (oracle/_ref/simple_knn) ----
+def simple_knn_available() -> bool:
+    import glob
+    return bool(glob.glob(os.path.join(REF_DIR, "simple_knn", "_C*.so")))
+
+
+def load_ref_simple_knn():
+    """distCUDA2 of the UNMODIFIED reference extension."""
+    import importlib.util
+    import glob
+    import torch  # noqa: F401  (the extension links against libtorch)
+    so = glob.glob(os.path.join(REF_DIR, "simple_knn", "_C*.so"))[0]
+    spec = importlib.util.spec_from_file_location("simple_knn._C", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.distCUDA2

@@ -22,7 +22,7 @@ def main():
     dev = torch.device("cuda:0")
     mod = ours if impl == "ours" else ref_ext.load()
     cloud = syn.make_cloud(P, seed=0).to(dev)
-    cam = syn.make_camera(W, H, (0, 0, 2.0)).to(dev)
+    cam = syn.waymo_ring(W, H, frames=50)[1].to(dev)      # bench.py's rank-0 view (front camera of frame 0)
     bg = torch.zeros(3, device=dev)
     g = torch.Generator(device=dev).manual_seed(1)
     gc = torch.randn(3, H, W, device=dev, generator=g)

@@ -57,6 +57,10 @@ def parse():
                          "HexPlane + decoder + rgb/depth pass + feat pass, fwd+bwd (BASELINE config 3 shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: force ncclAllReduce for the gradient bucket")
+    ap.add_argument("--peer-allreduce", action="store_true",
+                    help="N > 1: force the peer-memory reduce-scatter/all-gather kernels (default at N <= 3)")
     ap.add_argument("--no-train-iteration", action="store_true",
                     help="skip the whole-training-iteration leg (render + loss + stats + Adam, N == 1 only)")
     ap.add_argument("--cpu-sample", type=int, default=500_000)
@@ -159,9 +163,29 @@ def main():
         for v in leaves:
             v.grad = None
 
+    # gradient exchange of the view-parallel step.  Ours: reduce-scatter + all-gather kernels over NVLink peer
+    # memory (csrc/peer.cuh, dp.PeerAllReduce); reference arm and fallback: ncclAllReduce of the same flat bucket.
+    peer, peer_why = None, None
+    # measured on the 8-GPU box (profiles/r01h_*): the peer kernels beat NCCL at 2 GPUs (0.75 vs 0.89 ms for
+    # 472 MB), NCCL's in-switch (NVLS) reduction wins at 8 (1.18 vs 1.48 ms); default accordingly
+    use_peer = a.peer_allreduce or (world <= 3 and not a.nccl_allreduce)
+    if world > 1 and a.impl == "ours" and use_peer:
+        from s3gaussian_b200 import dp
+        n_grad = sum(v.numel() for v in leaves if v is not m2d)
+        peer, peer_why = dp.make_peer_all_reduce(n_grad, dev)
+        agree = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)          # all ranks take the same path
+        if int(agree[0]) == 0:
+            peer = None
+
     def allreduce_grads():
         if world > 1:
-            flat = torch.cat([v.grad.reshape(-1) for v in leaves if v is not m2d])
+            grads = [v.grad.reshape(-1) for v in leaves if v is not m2d]
+            if peer is not None:
+                n = sum(g_.numel() for g_ in grads)
+                torch.cat(grads, out=peer.flat(n))
+                return peer.all_reduce_()
+            flat = torch.cat(grads)
             dist.all_reduce(flat)
             return flat
         return None
@@ -366,7 +390,8 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{P} Gaussians ({'SH deg 3 in-kernel' if a.mode == 'sh' else 'precomputed colours'}), "
                                f"{W}x{H}, 1 view/GPU of the 50-frame ring, rasterizer fwd+bwd"
-                               + (", NCCL all-reduce of per-Gaussian grads" if world > 1 else ""),
+                               + ((", all-reduce of per-Gaussian grads over NVLink peer memory (own reduce-scatter/all-gather "
+                                   "kernels)" if peer is not None else ", NCCL all-reduce of per-Gaussian grads") if world > 1 else ""),
                    "points": P, "width": W, "height": H, "visible": V, "num_rendered": R,
                    "parallelism": f"view-parallel dp{world}",
                    "l2": "inputs (>= 470 MB of Gaussian parameters + sort arenas) exceed the 126 MB L2; no flush needed"},
@@ -374,7 +399,7 @@ def main():
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "what": "camera + GT image/depth H2D from pinned memory, render through the GaussianRasterizer API, "
                         "L1+depth-L2 loss, backward, loss D2H"},
-        "gpu_launches": (16 * a.steps) if a.impl == "ours" else 0,
+        "gpu_launches": ((16 + (2 if peer is not None else 0)) * a.steps) if a.impl == "ours" else 0,
         "clocks": clocks,
     }
     if a.impl == "reference":

@@ -339,6 +339,20 @@ int s3g_gather_rows(int n, const s3g_row_tensor* tensors, int64_t n_out, int64_t
 size_t s3g_knn_workspace_bytes(int P);
 int s3g_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* workspace, void* stream);
 
+/* ---- gradient all-reduce over peer-mapped memory -----------------------------------
+ * The view-parallel step ends with sum(grads) over ranks; the reference has no distributed code, the
+ * baseline is ncclAllReduce.  bufs: HOST array of `world` DEVICE pointers, bufs[p] = rank p's copy of the
+ * same symmetric float32 buffer of `numel` elements (multiple of 4), peer-mapped into this process
+ * (torch.distributed._symmetric_memory / cuMem VMM / cudaIpc).  Rank `rank` calls, on its own device:
+ *     <all ranks wrote their contribution; cross-rank barrier>
+ *     s3g_peer_reduce_scatter   - sums slice `rank` over all peers (direct NVLink loads) into bufs[rank]
+ *     <barrier>
+ *     s3g_peer_all_gather       - pulls the other reduced slices from their owners into bufs[rank]
+ *     <barrier before the buffer is written again>
+ * The kernels never wait on remote state; ordering is the caller's barriers (s3gaussian_b200/dp.py). */
+int s3g_peer_reduce_scatter(int world, int rank, const void* const* bufs, int64_t numel, void* stream);
+int s3g_peer_all_gather(int world, int rank, const void* const* bufs, int64_t numel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,62 @@
+// api_dp.cu - extern "C" entry points of the peer-memory gradient all-reduce (see include/s3g_b200.h).
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+
+#include "api_common.cuh"
+#include "peer.cuh"
+
+using namespace s3g;
+
+namespace {
+inline int fail(int code, const char* what, cudaError_t e = cudaSuccess) { return s3g::api_fail(code, what, e); }
+
+int peer_args(int world, int rank, const void* const* bufs, int64_t numel, PeerArgs& a) {
+    if (world < 2 || world > PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(S3G_ERR_ARG, "peer: 2 <= world <= 16, 0 <= rank < world");
+    if (!bufs || numel <= 0 || (numel & 3)) return fail(S3G_ERR_ARG, "peer: numel must be a positive multiple of 4");
+    for (int p = 0; p < world; ++p) {
+        if (!bufs[p] || ((uintptr_t)bufs[p] & 15)) return fail(S3G_ERR_ARG, "peer: null or misaligned buffer pointer");
+        a.buf[p] = static_cast<float*>(const_cast<void*>(bufs[p]));
+    }
+    a.world = world; a.rank = rank;
+    a.n4 = numel / 4;
+    a.chunk4 = (a.n4 + world - 1) / world;
+    return S3G_OK;
+}
+int peer_grid(long long work4) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (work4 + PEER_THREADS - 1) / PEER_THREADS;
+    return (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * 4));
+}
+}  // namespace
+
+extern "C" {
+
+int s3g_peer_reduce_scatter(int world, int rank, const void* const* bufs, int64_t numel, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PeerArgs a;
+    if (int rc = peer_args(world, rank, bufs, numel, a)) return rc;
+    const int grid = peer_grid(a.chunk4);
+    switch (world) {
+        case 2: peer_reduce_scatter_kernel<2><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        case 4: peer_reduce_scatter_kernel<4><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        case 8: peer_reduce_scatter_kernel<8><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        default: peer_reduce_scatter_kernel<0><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+    }
+    S3G_CUDA(cudaGetLastError(), "peer_reduce_scatter launch");
+    return S3G_OK;
+}
+
+int s3g_peer_all_gather(int world, int rank, const void* const* bufs, int64_t numel, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PeerArgs a;
+    if (int rc = peer_args(world, rank, bufs, numel, a)) return rc;
+    const int per = std::max(1, peer_grid(a.chunk4) / (world - 1) * 2);
+    peer_all_gather_kernel<<<dim3(per, world - 1), PEER_THREADS, 0, stream>>>(a);
+    S3G_CUDA(cudaGetLastError(), "peer_all_gather launch");
+    return S3G_OK;
+}
+
+}  // extern "C"

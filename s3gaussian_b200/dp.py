@@ -131,3 +131,71 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+def peer_slices(numel: int, world: int):
+    """[(begin, end)] in elements of the slice each rank reduces (float4 granularity, csrc/peer.cuh)."""
+    if numel % 4:
+        raise ValueError("peer all-reduce buffers hold a multiple of 4 floats")
+    n4 = numel // 4
+    chunk4 = (n4 + world - 1) // world
+    return [(min(r * chunk4, n4) * 4, min((r + 1) * chunk4, n4) * 4) for r in range(world)]
+
+
+class PeerAllReduce:
+    """SUM all-reduce of one flat fp32 buffer over NVLink peer memory with our own kernels
+    (csrc/peer.cuh): reduce-scatter by direct peer loads, then all-gather by direct peer loads.
+
+    The buffer is a symmetric allocation (torch.distributed._symmetric_memory: the same size on every rank,
+    peer-mapped into every process); rank order of the sum is fixed, so every rank gets bit-identical
+    results.  The kernels never wait on remote state - the three device-side barriers between them
+    (the handle's signal-pad barrier) provide the ordering:
+
+        contributions written | barrier | reduce-scatter | barrier | all-gather | barrier | buffer reusable
+
+    NCCL is the baseline this replaces for the 472 MB per-step gradient bucket; `available()`
+    tells whether the symmetric-memory rendezvous worked on this system (callers fall back to
+    dist.all_reduce and say so)."""
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.numel = (int(numel) + 3) // 4 * 4
+        self.group = group if group is not None else dist.group.WORLD
+        try:        # older torch releases need the group registered first; newer ones deprecate the call
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        ptrs = list(self.handle.buffer_ptrs)
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._lib = _lib
+        self.buffer.zero_()
+
+    def flat(self, numel: int | None = None) -> torch.Tensor:
+        return self.buffer if numel is None else self.buffer[:numel]
+
+    def all_reduce_(self) -> torch.Tensor:
+        import ctypes as C
+        lib = self._lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h = self.handle
+        h.barrier(channel=0)
+        self._lib.check(lib.s3g_peer_reduce_scatter(self.world, self.rank, self._ptrs, self.numel, stream),
+                        "s3g_peer_reduce_scatter")
+        h.barrier(channel=1)
+        self._lib.check(lib.s3g_peer_all_gather(self.world, self.rank, self._ptrs, self.numel, stream),
+                        "s3g_peer_all_gather")
+        h.barrier(channel=0)
+        return self.buffer
+
+
+def make_peer_all_reduce(numel: int, device):
+    """PeerAllReduce, or None (with the reason) where symmetric memory cannot be set up."""
+    try:
+        return PeerAllReduce(numel, device), None
+    except Exception as e:       # no NVLink peer access, old driver, non-NCCL group, ...
+        return None, f"{type(e).__name__}: {e}"

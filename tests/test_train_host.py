@@ -101,3 +101,26 @@ def test_gather_rows_argument_checks(built_lib):
     t = (_lib.RowTensor * 1)(_lib.RowTensor(1, 1, 3, 0))
     assert lib.s3g_gather_rows(1, t, 4, 5, None, None) == -1          # n_kept > n_out
     assert lib.s3g_gather_rows(1, t, 0, 0, None, None) == 0           # nothing to do
+
+
+def test_peer_slices_cover_the_buffer_in_float4_units():
+    from s3gaussian_b200.dp import peer_slices
+    for numel, world in ((40, 3), (8, 8), (118_000_000, 8), (4, 2), (472, 5)):
+        sl = peer_slices(numel, world)
+        assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == numel
+        assert all(b % 4 == 0 and e % 4 == 0 and b <= e for b, e in sl)
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        peer_slices(10, 2)
+
+
+def test_peer_entry_points_check_arguments(built_lib):
+    import ctypes as C
+    from s3gaussian_b200 import _lib
+    lib = _lib.load()
+    two = (C.c_void_p * 2)(16, 32)
+    assert lib.s3g_peer_reduce_scatter(1, 0, two, 8, None) == -1        # world < 2
+    assert lib.s3g_peer_reduce_scatter(2, 2, two, 8, None) == -1        # rank out of range
+    assert lib.s3g_peer_all_gather(2, 0, two, 6, None) == -1            # numel not a multiple of 4
+    bad = (C.c_void_p * 2)(16, 36)
+    assert lib.s3g_peer_all_gather(2, 0, bad, 8, None) == -1            # misaligned peer pointer

@@ -291,6 +291,11 @@ class GaussianModel:
             if st:
                 new_states[name] = (st["step"], add(st["exp_avg"], True), add(st["exp_avg_sq"], True))
         acc = None
+        P_old = self._xyz.shape[0]
+        have_acc = all(t.numel() > 0 and t.shape[0] == P_old for t in
+                       (self.xyz_gradient_accum, self.denom, self._deformation_accum, self.max_radii2D))
+        if keep_accumulators and not have_acc:      # training_setup() not called yet: nothing to carry over
+            keep_accumulators = False
         if keep_accumulators:
             acc = [add(self.xyz_gradient_accum, False), add(self.denom, False), add(self._deformation_accum, False),
                    add(self.max_radii2D.unsqueeze(1), False)]

@@ -24,6 +24,9 @@ COMPILE_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 OBJDIR = os.path.join(LIBDIR, "obj")
+# cicc 12.9 segfaults (4 runs out of 5, same source) in its -O3 pipeline on the backward decoder kernels; that
+# translation unit is built with the NVVM optimiser at -O2 (ptxas stays at -O3; measured: same kernel times)
+PER_FILE_FLAGS = {"api_deform_bwd.cu": ["-Xcicc", "-O2"]}
 
 
 def sources() -> list[str]:
@@ -44,16 +47,23 @@ def needs_build() -> bool:
 
 
 def _compile_one(nvcc: str, src: str, obj: str, verbose: bool) -> str:
-    cmd = [nvcc, *COMPILE_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+    """nvcc -c of one translation unit.  Should cicc crash on any other unit (see PER_FILE_FLAGS), that unit is
+    recompiled once with the NVVM optimiser at -O2 and the log says so."""
+    base = [nvcc, *COMPILE_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), []), "-I", os.path.join(ROOT, "include"),
+            "-c", "-o", obj, src]
     if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-    log = ""
-    for attempt in (1, 2):      # cicc 12.9 has crashed on this code base; the crash moves with tiny edits - retry once
+        base[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(base, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    if r.returncode != 0 and "Segmentation fault" in log:
+        cmd = base[:1] + ["-Xcicc", "-O2"] + base[1:]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = r.stdout + r.stderr
+        log = f"[build] cicc crashed at -O3 on {os.path.basename(src)}; recompiled with -Xcicc -O2\n" + r.stdout + r.stderr
         if r.returncode == 0:
-            return log
-    raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{log}")
+            print(log.splitlines()[0], file=sys.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{log}")
+    return log
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -1070,7 +1070,7 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
 // sum the per-CTA partial Linear gradients: one thread per gradient element
 struct ReduceSeg { float* dst; int off; int count; };
 struct ReduceArgs { ReduceSeg seg[32]; int nseg; const float* partial; int stride; int nparts; };
-__global__ void __launch_bounds__(256) deform_reduce_kernel(ReduceArgs r) {
+static __global__ void __launch_bounds__(256) deform_reduce_kernel(ReduceArgs r) {
     const ReduceSeg sg = r.seg[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sg.count) return;

@@ -2,7 +2,7 @@
   python tools/dev_train.py [--points 2000000] [--width 1920 --height 1280]"""
 import argparse, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch
 from s3gaussian_b200 import losses, optim
 
@@ -132,4 +132,33 @@ def torch_reg():     # the same torch statements the reference runs (oracle rest
 
 
 out["plane_regulation"] = {"ours_ms": timeit(ours_reg), "torch_ms": timeit(torch_reg)}
+
+# ---- 3-NN scale initialiser ------------------------------------------------------------------------
+from s3gaussian_b200.simple_knn import distCUDA2
+import make_golden_knn as mk
+pts = mk.knn_inputs("clustered", P, 12).to(dev)
+res = {"points": P, "ours_ms": timeit(lambda: distCUDA2(pts), iters=3, warm=1)}
+if _re.simple_knn_available():
+    ref_knn = _re.load_ref_simple_knn()
+    res["reference_ms"] = timeit(lambda: ref_knn(pts), iters=3, warm=1)
+    res["bit_exact"] = bool(torch.equal(distCUDA2(pts), ref_knn(pts)))
+out["knn_init"] = res
+
+# ---- densify + prune on the model ------------------------------------------------------------------
+from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params
+cl = syn.make_cloud(P, seed=0)
+gm = GaussianModel(3).create_from_tensors(cl.xyz.to(dev), cl.features_dc.to(dev), cl.features_rest.to(dev),
+                                          cl.scaling.to(dev), cl.rotation.to(dev), cl.opacity.to(dev))
+gm.training_setup(default_optimization_params())
+for n_ in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"):
+    getattr(gm, n_).grad = torch.zeros_like(getattr(gm, n_))
+gm.optimizer.step()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+gm.xyz_gradient_accum = torch.rand(P, 1, device=dev) * 4e-4
+gm.denom = torch.ones(P, 1, device=dev)
+torch.cuda.synchronize(); e0.record()
+gm.densify(0.0002, 0.005, 30.0, None)
+gm.prune(0.0002, 0.005, 30.0, None)
+e1.record(); torch.cuda.synchronize()
+out["densify_prune"] = {"ours_ms": e0.elapsed_time(e1), "points_before": P, "points_after": int(gm.get_xyz.shape[0])}
 print(json.dumps(out))

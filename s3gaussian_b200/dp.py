@@ -163,15 +163,15 @@ class PeerAllReduce:
         from . import _lib
         self.numel = (int(numel) + 3) // 4 * 4
         self.group = group if group is not None else dist.group.WORLD
-        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
-        try:
-            self.handle = symm_mem.rendezvous(self.buffer, self.group)
-        except Exception:      # older torch releases need the group registered first (newer ones deprecate the call)
-            import warnings
+        import warnings
+        try:        # older torch releases need the group registered first; newer ones deprecate the call (warning muted)
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 symm_mem.enable_symm_mem_for_group(self.group.group_name)
-            self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        except Exception:
+            pass
+        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
         self.rank, self.world = self.handle.rank, self.handle.world_size
         ptrs = list(self.handle.buffer_ptrs)
         self._ptrs = (C.c_void_p * self.world)(*ptrs)

@@ -39,6 +39,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same, with the operand majors chosen per operand: bit 15 / bit 16 of the instruction descriptor select
+// MN-major ("transposed") A / B.  A canonical K-major tile X[R][K] read as an MN-major operand is X^T:
+//   MN index = k (4 contiguous elements, groups of 4 every 128 bytes  -> SBO' = 128),
+//   K  index = r (8 rows 16 bytes apart = one core matrix; next 8-row group (K/4)*128 bytes on -> LBO').
+// One MMA consumes K' = 8 rows; the descriptor start address advances by (K/4)*128 bytes per k-step.
+// (Used by the weight-gradient products delta^T * act of the backward decoder; NOT yet run on hardware -
+// tools/dev_umma.py --mn is the first thing to run in round 2.)
+__host__ __device__ constexpr uint32_t make_idesc_tf32_major(int M, int N, bool a_mn, bool b_mn) {
+    return make_idesc_tf32(M, N) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16);
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

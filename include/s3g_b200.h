@@ -355,6 +355,9 @@ int s3g_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* work
  * The kernels never wait on remote state; ordering is the caller's barriers (s3gaussian_b200/dp.py). */
 int s3g_peer_reduce_scatter(int world, int rank, const void* const* bufs, int64_t numel, void* stream);
 int s3g_peer_all_gather(int world, int rank, const void* const* bufs, int64_t numel, void* stream);
+/* NVLS variant: one kernel on the MULTICAST address of the same symmetric buffer (multimem.ld_reduce +
+ * multimem.st on slice `rank`), barriers before and after as above.  Written for round 2, not yet measured. */
+int s3g_peer_nvls_all_reduce(int world, int rank, void* multicast_ptr, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

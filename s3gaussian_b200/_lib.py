@@ -57,6 +57,7 @@ SIGNATURES = {
     "s3g_knn_mean_dist2": (_I, [_I, _V, _V, _V, _V]),
     "s3g_peer_reduce_scatter": (_I, [_I, _I, _V, _I64, _V]),
     "s3g_peer_all_gather": (_I, [_I, _I, _V, _I64, _V]),
+    "s3g_peer_nvls_all_reduce": (_I, [_I, _I, _V, _I64, _V]),
     "s3g_gather_rows": (_I, [_I, _V, _I64, _I64, _V, _V]),
     "s3g_plane_reg_workspace_bytes": (_SZ, [_I, _V]),
     "s3g_plane_reg_forward": (_I, [_I, _V, _V, _V, _V]),

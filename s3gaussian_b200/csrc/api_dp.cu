@@ -59,4 +59,15 @@ int s3g_peer_all_gather(int world, int rank, const void* const* bufs, int64_t nu
     return S3G_OK;
 }
 
+int s3g_peer_nvls_all_reduce(int world, int rank, void* multicast_ptr, int64_t numel, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (world < 2 || world > PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(S3G_ERR_ARG, "peer: 2 <= world <= 16, 0 <= rank < world");
+    if (!multicast_ptr || ((uintptr_t)multicast_ptr & 15) || numel <= 0 || (numel & 3))
+        return fail(S3G_ERR_ARG, "peer_nvls: multicast pointer must be 16-byte aligned, numel a positive multiple of 4");
+    const long long n4 = numel / 4, chunk4 = (n4 + world - 1) / world;
+    peer_nvls_all_reduce_kernel<<<peer_grid(chunk4), PEER_THREADS, 0, stream>>>(static_cast<float*>(multicast_ptr), rank, n4, chunk4);
+    S3G_CUDA(cudaGetLastError(), "peer_nvls_all_reduce launch");
+    return S3G_OK;
+}
+
 }  // extern "C"

@@ -63,4 +63,24 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_all_gather_kernel(const __g
     for (; i < hi; i += stride) dst[i] = ld_peer(src + i);
 }
 
+// ---- NVLS variant (in-switch reduction), one kernel ---------------------------------------------------------
+// mc = the multicast address of the symmetric buffer (every rank's copy behind one pointer).  Rank r owns slice
+// r: multimem.ld_reduce returns the SUM over all ranks of the addressed 16 bytes (the NVSwitch reduces),
+// multimem.st writes the result into every rank's copy.  Half the NVLink traffic of the peer-load version.
+// NOT yet run on hardware (written at the end of round 1 without GPU budget; tools/dev_peer.py --nvls checks
+// it against NCCL and times it) - bench.py does not use it.
+__global__ void __launch_bounds__(PEER_THREADS) peer_nvls_all_reduce_kernel(float* mc, int rank, long long n4,
+                                                                           long long chunk4) {
+    const long long lo = (long long)rank * chunk4;
+    const long long hi = (lo + chunk4 < n4) ? lo + chunk4 : n4;
+    for (long long i = lo + (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i < hi; i += (long long)gridDim.x * PEER_THREADS) {
+        float4 v;
+        float* p = mc + 4 * i;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+
 }  // namespace s3g

@@ -178,6 +178,21 @@ class PeerAllReduce:
         self._lib = _lib
         self.buffer.zero_()
 
+    def nvls_all_reduce_(self) -> torch.Tensor:
+        """In-switch (NVLS) variant: one kernel on the handle's multicast pointer.  Round-2 code path: not yet
+        run on hardware, nothing calls it by default (tools/dev_peer.py --nvls)."""
+        import ctypes as C
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("PeerAllReduce: this symmetric allocation has no multicast mapping")
+        lib = self._lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.handle.barrier(channel=0)
+        self._lib.check(lib.s3g_peer_nvls_all_reduce(self.world, self.rank, C.c_void_p(mc), self.numel, stream),
+                        "s3g_peer_nvls_all_reduce")
+        self.handle.barrier(channel=1)
+        return self.buffer
+
     def flat(self, numel: int | None = None) -> torch.Tensor:
         return self.buffer if numel is None else self.buffer[:numel]
 

@@ -52,6 +52,17 @@ def timeit(fn, iters=10):
     return float(t[0])
 
 
+if "--nvls" in sys.argv:      # round-2 path: in-switch reduction through the multicast mapping
+    x = torch.randn(numel, device=dev, generator=g)
+    ref = x.clone(); dist.all_reduce(ref)
+    par.flat(numel).copy_(x)
+    out = par.nvls_all_reduce_()[:numel]
+    torch.cuda.synchronize()
+    err = float((out - ref).abs().max() / (ref.abs().max() + 1e-30))
+    t_nvls = timeit(par.nvls_all_reduce_)
+    if rank == 0:
+        print(json.dumps({"nvls_rel_err_vs_nccl": err, "nvls_ms": round(t_nvls, 4)}))
+
 x = torch.randn(numel, device=dev)
 t_peer = timeit(par.all_reduce_)
 t_nccl = timeit(lambda: dist.all_reduce(x))

@@ -1,6 +1,5 @@
 // api_deform_bwd.cu - extern "C" entry points of the fused HexPlane + decoder stage, backward (see include/s3g_b200.h).
 #include "deform_host.cuh"
-#include "deform_tc_bwd.cuh"
 
 using namespace s3g;
 
@@ -28,32 +27,8 @@ int bwd_grid(int ntiles) {
 }
 constexpr int kMaxBwdGrid = 256;
 
-// ---- tcgen05 backward decoder (DRAFT, deform_tc_bwd.cuh): only with S3G_TC_BWD=1 in the environment ----------
-constexpr size_t kTcBwdPrepFloats = (size_t)BW_COUNT * 2 * 64 * 64;     // every prepared entry is at most 64 x 64, hi + lo
-bool tc_bwd_requested() {
-    static const bool on = [] { const char* e = std::getenv("S3G_TC_BWD"); return e && e[0] == '1'; }();
-    return on;
-}
-bool tc_bwd_supported(const DNet& d) {
-    return d.L == 4 && d.pos.w1 && d.shs.w1 && d.w_d0 && !d.scl.w1 && !d.rot.w1 && !d.opa.w1;
-}
-void tc_bwd_table(const DNet& d, BwPrepArgs& p) {
-    int t = 0;
-    auto add = [&](int e, const float* src, int stride, int col0, bool tr, int n, int k, int n_valid) {
-        p.src[e] = src; p.stride[e] = stride; p.col0[e] = col0; p.transpose[e] = tr ? 1 : 0; p.n_valid[e] = n_valid;
-        p.tab.off[e] = t; p.tab.n[e] = n; p.tab.k[e] = k;
-        t += 2 * n * k;
-    };
-    add(BW_FA, d.w_feat, 128, 0, false, 64, 64, 64);   add(BW_FB, d.w_feat, 128, 64, false, 64, 64, 64);
-    add(BW_D0, d.w_d0, 64, 0, false, 64, 64, 64);      add(BW_D2, d.w_d2, 64, 0, false, 64, 64, 64);
-    add(BW_S1, d.shs.w1, 64, 0, false, 64, 64, 64);    add(BW_S2, d.shs.w2, 64, 0, false, 48, 64, 48);
-    add(BW_P1, d.pos.w1, 64, 0, false, 64, 64, 64);
-    add(BW_D2T, d.w_d2, 64, 0, true, 64, 64, 64);      add(BW_D0T, d.w_d0, 64, 0, true, 64, 64, 64);
-    add(BW_S2T, d.shs.w2, 64, 0, true, 64, 48, 64);    // E[n][k] = W_s2[k][n]: 64 x 48
-    add(BW_S1T, d.shs.w1, 64, 0, true, 64, 64, 64);    add(BW_P1T, d.pos.w1, 64, 0, true, 64, 64, 64);
-    add(BW_FAT, d.w_feat, 128, 0, true, 64, 64, 64);   add(BW_FBT, d.w_feat, 128, 64, true, 64, 64, 64);
-    p.tab.total = t;
-}
+// ---- tcgen05 backward decoder (DRAFT, own translation unit api_deform_tc_bwd.cu): only with S3G_TC_BWD=1 -----
+constexpr size_t kTcBwdPrepFloats = (size_t)14 * 2 * 64 * 64;     // prepared weights of the draft (14 entries <= 64 x 64, hi + lo)
 }  // namespace
 
 extern "C" {
@@ -130,28 +105,11 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
     if (P > 0) {
         const size_t smem = DeformBwdSmem::floats(d.L) * sizeof(float);
         if (smem > 227 * 1024) return fail(S3G_ERR_UNSUPPORTED, "deform_backward: too many levels for shared memory");
-        if (tc_bwd_requested() && tc_bwd_supported(d)) {
-            // DRAFT path (never validated on hardware): prepared weights behind dfeatures in the workspace
-            BwPrepArgs prep;
-            tc_bwd_table(d, prep);
-            float* wprep = a.dfeatures + (size_t)P * FD * d.L;
-            wprep = reinterpret_cast<float*>(((uintptr_t)wprep + 255) & ~(uintptr_t)255);
-            prep.dst = wprep;
-            bw_prep_weights_kernel<<<dim3(8, BW_COUNT), 256, 0, stream>>>(prep);
-            DeformTcBwdArgs t;
-            t.net = a.net; t.P = P; t.xyz = xyz; t.scales = scales; t.rot = rotations; t.opacity = opacity; t.shs = shs;
-            t.campos = campos; t.sh_degree = sh_degree; t.features = features;
-            t.g_means = g_means3D; t.g_scales = g_scales_act; t.g_rot = g_rot_act; t.g_opacity = g_opacity_act;
-            t.g_colors = g_colors; t.g_dx = g_dx; t.g_dshs = g_dshs; t.g_feat = g_feat;
-            t.d_scales = d_scales; t.d_rot = d_rotations; t.d_opacity = d_opacity; t.d_shs = d_shs;
-            t.dxyz_direct = d_xyz; t.dfeatures = a.dfeatures; t.partial = a.partial; t.off = a.off;
-            t.wprep = wprep; t.tab = prep.tab;
-            const size_t tsmem = (size_t)(3 * BW_TILE_FLOATS + 2 * 64 * 64) * sizeof(float);
-            S3G_CUDA(cudaFuncSetAttribute(deform_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem), "deform tc bwd smem attr");
-            const int tgrid = bwd_grid((P + BWM - 1) / BWM);
-            grid = tgrid;      // number of partial buffers the reduction sums
+        int tgrid = 0;
+        if (tc_bwd_launch(a, kMaxBwdGrid, stream, &tgrid)) {       // DRAFT path, see api_deform_tc_bwd.cu
+            if (tgrid < 0) return tgrid;
+            grid = tgrid;
             r.nparts = tgrid;
-            deform_backward_tc_kernel<<<tgrid, BWM, tsmem, stream>>>(t);
         } else if (d.L == 4) {
             S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
             deform_backward_kernel<4><<<grid, DTHREADS, smem, stream>>>(a);

@@ -109,6 +109,27 @@ class ClockSampler:
 ref_ext_mod = None
 
 
+def count_launches(fn):
+    """(kernels of libs3g_b200.so, all kernels) launched by one call of fn(), counted by CUPTI through
+    torch.profiler in a separate untimed pass; (None, None) if the profiler is unavailable."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        ours = total = 0
+        for ev in prof.events():
+            if str(getattr(ev, "device_type", "")).endswith("CUDA") and ev.name and not ev.name.startswith(("Memcpy", "Memset", "cuda")):
+                total += 1
+                if "s3g::" in ev.name:
+                    ours += 1
+        return ours, total
+    except Exception:
+        return None, None
+
+
 def load_impl(name):
     if name == "ours":
         from s3gaussian_b200 import build
@@ -206,16 +227,28 @@ def main():
     h2d_bytes = gt_img.numel() * 4 + gt_dep.numel() * 4 + cam_host.numel() * 4
     loss_host = torch.zeros(1).pin_memory()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = torch.cuda.Event()
+
     def step_e2e():
         zero_grads()
-        cam_d = cam_host.to(dev, non_blocking=True)
-        img_d = gt_img.to(dev, non_blocking=True)
-        dep_d = gt_dep.to(dev, non_blocking=True)
+        main = torch.cuda.current_stream()
+        cam_d = cam_host.to(dev, non_blocking=True)       # 140 bytes, needed by the first kernel
+        # the ground-truth image / depth are first needed at the loss: their H2D copies run on a copy stream
+        # underneath the forward pass (same step function for both arms)
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            img_d = gt_img.to(dev, non_blocking=True)
+            dep_d = gt_dep.to(dev, non_blocking=True)
+            copied.record(copy_stream)
         rs = settings._replace(viewmatrix=cam_d[:16].view(4, 4), projmatrix=cam_d[16:32].view(4, 4), campos=cam_d[32:35])
         r = mod.GaussianRasterizer(rs)
         color, radii, depth = r(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"],
                                 colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"],
                                 cov3D_precomp=None)
+        main.wait_event(copied)
+        img_d.record_stream(main)
+        dep_d.record_stream(main)
         loss = (color - img_d).abs().mean() + 0.5 * ((depth - dep_d) ** 2).mean()
         loss.backward()
         allreduce_grads()
@@ -245,7 +278,7 @@ def main():
 
     if a.impl == "ours":
         from s3gaussian_b200 import _lib
-        _lib.profile_enable(True)
+        _lib.profile_enable(False)      # the timed loops run the product build: no per-stage events
     sampler = ClockSampler(local) if (rank == 0 and not a.no_clocks) else None
     if sampler:
         sampler.start()
@@ -256,6 +289,7 @@ def main():
     radii = step_resident()
     torch.cuda.synchronize()
     V = int((radii > 0).sum())
+    launches_ours, launches_all = count_launches(step_resident)
 
     # ---- roofline of the dominant kernel ----------------------------------
     roofline, stages = None, None
@@ -267,9 +301,18 @@ def main():
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     R = None
+    if a.impl == "reference":
+        E = torch.Tensor([])
+        gg = lambda k: d[k].to(dev).contiguous() if d[k] is not None else E
+        R = int(mod._C.rasterize_gaussians(d["bg"].to(dev), gg("means3D"), gg("colors_precomp"), gg("opacities"),
+                                           gg("scales"), gg("rotations"), 1.0, gg("cov3D_precomp"),
+                                           d["viewmatrix"].to(dev), d["projmatrix"].to(dev), d["tanfovx"], d["tanfovy"],
+                                           H, W, gg("shs"), 3, d["campos"].to(dev), False, False)[0])
     if a.impl == "ours":
         from s3gaussian_b200 import _lib
         acc_f, acc_b, n = {}, {}, 5
+        _lib.profile_enable(True)       # separate, untimed pass: per-stage CUDA events on the launching stream
+        step_resident()
         for _ in range(n):
             step_resident()
             torch.cuda.synchronize()
@@ -390,8 +433,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{P} Gaussians ({'SH deg 3 in-kernel' if a.mode == 'sh' else 'precomputed colours'}), "
                                f"{W}x{H}, 1 view/GPU of the 50-frame ring, rasterizer fwd+bwd"
-                               + ((", all-reduce of per-Gaussian grads over NVLink peer memory (own reduce-scatter/all-gather "
-                                   "kernels)" if peer is not None else ", NCCL all-reduce of per-Gaussian grads") if world > 1 else ""),
+                               + (", all-reduce of per-Gaussian grads" if world > 1 else ""),
+                   "collective": (("NVLink peer-memory reduce-scatter/all-gather kernels (csrc/peer.cuh)" if peer is not None
+                                   else "ncclAllReduce") if world > 1 else None),
                    "points": P, "width": W, "height": H, "visible": V, "num_rendered": R,
                    "parallelism": f"view-parallel dp{world}",
                    "l2": "inputs (>= 470 MB of Gaussian parameters + sort arenas) exceed the 126 MB L2; no flush needed"},
@@ -399,7 +443,10 @@ def main():
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "what": "camera + GT image/depth H2D from pinned memory, render through the GaussianRasterizer API, "
                         "L1+depth-L2 loss, backward, loss D2H"},
-        "gpu_launches": ((16 + (2 if peer is not None else 0)) * a.steps) if a.impl == "ours" else 0,
+        # kernels of libs3g_b200.so per step x steps, counted by CUPTI in an untimed pass (all kernels incl. torch
+        # glue in gpu_launches_all)
+        "gpu_launches": (launches_ours * a.steps if launches_ours is not None else None) if a.impl == "ours" else 0,
+        "gpu_launches_all": launches_all * a.steps if launches_all is not None else None,
         "clocks": clocks,
     }
     if a.impl == "reference":

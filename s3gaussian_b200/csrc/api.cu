@@ -393,7 +393,17 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
         ra.bg = background; ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb;
         ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
         ra.dL_dpix = dL_dpix; ra.dL_dpix_depth = dL_dpix_depth; ra.grad_rec = geom.grad_rec;
-        render_backward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+        // > 48 KB of dynamic shared memory needs the opt-in, once per device
+        static unsigned long long attr_done = 0;
+        int devid = 0;
+        S3G_CUDA(cudaGetDevice(&devid), "cudaGetDevice");
+        if (devid >= 64 || !((attr_done >> devid) & 1ull)) {
+            S3G_CUDA(cudaFuncSetAttribute(render_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(RenderBwdSmem)),
+                     "render_backward smem attribute");
+            if (devid < 64) attr_done |= 1ull << devid;
+        }
+        render_backward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, sizeof(RenderBwdSmem), stream>>>(ra);
         S3G_STAGE("render_backward");
     }
 

@@ -70,8 +70,8 @@ struct SortTemp {
 // Per-Gaussian state (P-indexed).
 struct GeomState {
     float4* xyAB;            // {pix.x, pix.y, conic.x, conic.y}          (forward.cu:252-254)
-    float4* Cod;             // {conic.z, opacity, view depth, tau_cull}
-    float4* rgb;             // {r,g,b,_} SH colour or copy of colors_precomp (forward.cu:243-246)
+    float4* Cod;             // {conic.z, opacity, tau_cull, own index (bits)}
+    float4* rgb;             // {r,g,b, view depth}: SH colour or copy of colors_precomp (forward.cu:243-246)
     uint32_t* depth_key;     // float bits of depth, or DEPTH_KEY_INVISIBLE
     uint32_t* tiles_touched; // forward.cu:255
     ushort4* rect;           // {min.x, min.y, max.x, max.y} of getRect (auxiliary.h:46-56)

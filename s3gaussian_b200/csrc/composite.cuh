@@ -17,10 +17,10 @@
 //    (forward.cu:328-366) is what makes it issue-bound;
 //  * a warp leaves the loop as soon as all its pixels are saturated, the block
 //    as soon as all warps are;
-//  * backward: per surviving instance the 32 pixel partials of the 10 gradient
-//    components are reduced with a 12-shuffle split butterfly and land as ONE
-//    10-lane RED on a 64-byte record, instead of 10 atomics per (pixel,
-//    Gaussian) pair (backward.cu:550-587).
+//  * backward: two phases per warp - lane = pixel for the sequential recurrences, then
+//    lane = instance for the sums over pixels (moments of X = G dL/dalpha in registers) -
+//    and three vector REDs per (warp, instance) instead of 10 atomics per (pixel,
+//    Gaussian) pair (backward.cu:550-587); see render_backward_kernel.
 #pragma once
 #include "common.cuh"
 
@@ -74,8 +74,8 @@ struct RenderFwdArgs {
 // quarter-warp.
 struct __align__(16) Rec {
     float4 a;   // pix.x, pix.y, conic.x, conic.y
-    float4 b;   // conic.z, opacity, depth, tau_cull
-    float4 c;   // r, g, b, -
+    float4 b;   // conic.z, opacity, tau_cull, own index (bits)
+    float4 c;   // r, g, b, depth
 };
 
 __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs a) {
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
                     const float4 g1 = rec[j].b;
                     const float q = rect_min_q(g0.z, g0.w, g1.x, g0.x - rx1, g0.x - rx0,
                                                g0.y - ry1, g0.y - ry0);
-                    pass = !(q > g1.w);
+                    pass = !(q > g1.z);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
                 const uint32_t idx_base = (uint32_t)(b * CB + c0 + 1);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
                     C0 += col.x * ae * T;
                     C1 += col.y * ae * T;
                     C2 += col.z * ae * T;
-                    D += g1.z * ae * T;
+                    D += col.w * ae * T;
                     T = blend ? test_T : T;
                     last_contributor = blend ? idx_base + (uint32_t)bit : last_contributor;
                     alive = alive && !stop;
@@ -204,71 +204,109 @@ struct RenderBwdArgs {
     float* grad_rec;             // [P][GRAD_REC], zeroed
 };
 
-// 10 per-lane partials -> 10 warp sums, each left in one even lane:
-// lanes {0,2,4,8,10} hold v0..v4, lanes {16,18,20,24,26} hold v5..v9.
-__device__ __forceinline__ float warp_reduce10(const float (&v)[10], int lane) {
-    const uint32_t F = 0xffffffffu;
-    float r[5];
-    const bool h4 = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float send = h4 ? v[i] : v[i + 5];
-        const float keep = h4 ? v[i + 5] : v[i];
-        r[i] = keep + __shfl_xor_sync(F, send, 16);
-    }
-    const bool h3 = lane & 8;
-    float s0, s1, s2;
-    {
-        float send = h3 ? r[0] : r[3], keep = h3 ? r[3] : r[0];
-        s0 = keep + __shfl_xor_sync(F, send, 8);
-        send = h3 ? r[1] : r[4]; keep = h3 ? r[4] : r[1];
-        s1 = keep + __shfl_xor_sync(F, send, 8);
-        send = h3 ? r[2] : 0.f; keep = h3 ? 0.f : r[2];
-        s2 = keep + __shfl_xor_sync(F, send, 8);
-    }
-    const bool h2 = lane & 4;
-    float t0, t1;
-    {
-        float send = h2 ? s0 : s2, keep = h2 ? s2 : s0;
-        t0 = keep + __shfl_xor_sync(F, send, 4);
-        send = h2 ? s1 : 0.f; keep = h2 ? 0.f : s1;
-        t1 = keep + __shfl_xor_sync(F, send, 4);
-    }
-    const bool h1 = lane & 2;
-    float u;
-    {
-        const float send = h1 ? t0 : t1, keep = h1 ? t1 : t0;
-        u = keep + __shfl_xor_sync(F, send, 2);
-    }
-    u += __shfl_xor_sync(F, u, 1);
-    return u;
-}
-// slot (0..9) owned by `lane` after warp_reduce10, or -1
-__device__ __forceinline__ int reduce10_slot(int lane) {
-    if (lane & 1) return -1;
-    const int code = (lane >> 1) & 7;   // (b3,b2,b1)
-    int r;
-    switch (code) {
-        case 0: r = 0; break;
-        case 1: r = 1; break;
-        case 2: r = 2; break;
-        case 4: r = 3; break;
-        case 5: r = 4; break;
-        default: return -1;
-    }
-    return r + ((lane & 16) ? 5 : 0);
-}
-
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// one 16-byte / 8-byte reduction into a gradient record instead of four / two scalar REDs
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// ---- backward composite -----------------------------------------------------
+// Two phases per warp (8x4 pixel rectangle), both without a cross-lane reduction per instance:
+//
+//  phase 1, lane = pixel (sequential in the list, as backward.cu:513-589): for every instance that survives the
+//    rectangle cull the lane advances its pixel's T / accumulated-colour recurrences and leaves exactly two
+//    numbers in shared memory: X = G * dL/dalpha and w = alpha * T.  Every per-Gaussian gradient the reference
+//    accumulates with 10 atomics per (pixel, Gaussian) is linear in those two with pixel-only coefficients:
+//        dL/dopacity = sum X            dL/dconic  = -0.5 o sum X (dx^2, dx dy, dy^2)
+//        dL/dmean2D  = o sum X (-A dx - B dy, -C dy - B dx) * (W/2, H/2)
+//        dL/dcolour_c = sum w dL/dpix_c        dL/ddepth = sum w dL/dpix_depth
+//  phase 2, lane = (instance slot, half of the rectangle): after BKS survivors the roles flip - every lane walks
+//    16 pixels of ONE instance, accumulating the six pixel-coordinate moments of X (separable: three per pixel,
+//    six per row) and the four w * dL/dpix sums in registers; the halves meet with 10 shuffles, the moments are
+//    shifted to the Gaussian's centre and land as three vector REDs per instance.
+//
+// Per surviving (warp, instance) that is ~12 issue slots of reduction instead of the 46-instruction shuffle
+// butterfly + selects of a per-instance warp reduction.
+constexpr int BCB = 128;          // instances per staged batch (backward)
+constexpr int BKS = 16;           // survivor slots per warp
+constexpr int BXW_STRIDE = 33;    // float2 row stride of the slot table: conflict-free for both phases
+
+struct RenderBwdSmem {
+    Rec rec[2][BCB];                       // 12 KB
+    float2 xw[8][BKS][BXW_STRIDE];         // 33 KB  {X, w} per (slot, pixel)
+    float4 slot_a[8][BKS];                 // {pix.x, pix.y, conic.x, conic.y}
+    float4 slot_b[8][BKS];                 // {conic.z, opacity, -, id bits}
+    float4 dpix[8][32];                    // dL/dpix {r, g, b, depth} of the warp's pixels
+    uint32_t max_contrib;
+};
+
+__device__ __forceinline__ void bwd_flush(const RenderBwdSmem& sm, int warp, int lane, int ns, float cx, float cy,
+                                          float ddelx_dx, float ddely_dy, float* __restrict__ grad_rec) {
+    const int j = lane & (BKS - 1), h = lane >> 4;
+    const float2* row = &sm.xw[warp][j][h * 16];
+    const float4* dp = &sm.dpix[warp][h * 16];
+    float m00 = 0.f, m10 = 0.f, m20 = 0.f, m01 = 0.f, m11 = 0.f, m02 = 0.f;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, cd = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const float2 v = row[rr * 8 + x];
+            const float4 d = dp[rr * 8 + x];
+            const float xc = (float)x - 3.5f;        // pixel x relative to the rectangle centre
+            r0 += v.x;
+            r1 = fmaf(v.x, xc, r1);
+            r2 = fmaf(v.x, xc * xc, r2);
+            c0 = fmaf(v.y, d.x, c0);
+            c1 = fmaf(v.y, d.y, c1);
+            c2 = fmaf(v.y, d.z, c2);
+            cd = fmaf(v.y, d.w, cd);
+        }
+        const float yc = (float)(2 * h + rr) - 1.5f;
+        m00 += r0; m10 += r1; m20 += r2;
+        m01 = fmaf(yc, r0, m01);
+        m11 = fmaf(yc, r1, m11);
+        m02 = fmaf(yc * yc, r0, m02);
+    }
+    const uint32_t F = 0xffffffffu;
+    m00 += __shfl_xor_sync(F, m00, 16); m10 += __shfl_xor_sync(F, m10, 16); m20 += __shfl_xor_sync(F, m20, 16);
+    m01 += __shfl_xor_sync(F, m01, 16); m11 += __shfl_xor_sync(F, m11, 16); m02 += __shfl_xor_sync(F, m02, 16);
+    c0 += __shfl_xor_sync(F, c0, 16); c1 += __shfl_xor_sync(F, c1, 16);
+    c2 += __shfl_xor_sync(F, c2, 16); cd += __shfl_xor_sync(F, cd, 16);
+    if (j < ns) {
+        const float4 ga = sm.slot_a[warp][j];
+        const float4 gb = sm.slot_b[warp][j];
+        // d = xy - pix = e - (pixel - centre)
+        const float ex = ga.x - cx, ey = ga.y - cy;
+        const float sx = ex * m00 - m10;
+        const float sy = ey * m00 - m01;
+        const float sxx = fmaf(ex, ex * m00 - 2.f * m10, m20);
+        const float syy = fmaf(ey, ey * m00 - 2.f * m01, m02);
+        const float sxy = fmaf(ex, ey * m00 - m01, m11 - ey * m10);
+        const float o = gb.y, hf = -0.5f * o;
+        float* g = grad_rec + (size_t)__float_as_uint(gb.w) * GRAD_REC;
+        if (h == 0) {
+            red_add_v4(g, o * ddelx_dx * (-ga.z * sx - ga.w * sy), o * ddely_dy * (-gb.x * sy - ga.w * sx), hf * sxx,
+                       hf * sxy);
+            red_add_v2(g + 8, c2, cd);
+        } else {
+            red_add_v4(g + 4, hf * syy, m00, c0, c1);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs a) {
-    __shared__ Rec s_rec[2][CB];
-    __shared__ uint32_t s_id[2][CB];
-    __shared__ uint32_t s_max;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    RenderBwdSmem& sm = *reinterpret_cast<RenderBwdSmem*>(s_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -280,6 +318,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
     const uint32_t pix_id = (uint32_t)a.W * py + px;
     const float rx0 = (float)X0, rx1 = (float)(X0 + SUB_W - 1);
     const float ry0 = (float)Y0, ry1 = (float)(Y0 + SUB_H - 1);
+    const float cx = (float)X0 + 3.5f, cy = (float)Y0 + 1.5f;
     const size_t HW = (size_t)a.H * a.W;
 
     const uint2 range = a.ranges[tile];
@@ -294,71 +333,72 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
         dpix2 = a.dL_dpix[2 * HW + pix_id];
         dpixd = a.dL_dpix_depth[pix_id];
     }
+    sm.dpix[warp][lane] = make_float4(dpix0, dpix1, dpix2, dpixd);
     // -(T_final * sum_c bg_c dL/dpix_c): the background term of backward.cu:564-567
     const float nbg = -T_final * (a.bg[0] * dpix0 + a.bg[1] * dpix1 + a.bg[2] * dpix2);
 
     // only instances below the block's deepest contributor matter (backward.cu:513)
-    if (tid == 0) s_max = 0;
+    if (tid == 0) sm.max_contrib = 0;
     __syncthreads();
     const int warp_max = (int)__reduce_max_sync(0xffffffffu, (uint32_t)last_contributor);
-    if (lane == 0 && warp_max > 0) atomicMax(&s_max, (uint32_t)warp_max);
+    if (lane == 0 && warp_max > 0) atomicMax(&sm.max_contrib, (uint32_t)warp_max);
     __syncthreads();
-    const int m = (int)s_max;   // instances [0, m) are walked back to front
-    const int nb = (m + CB - 1) / CB;
+    const int m = (int)sm.max_contrib;   // instances [0, m) are walked back to front
+    const int nb = (m + BCB - 1) / BCB;
     if (nb == 0) return;
 
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_depth = 0.f;
+    // per-pixel recurrences of backward.cu:529-563.  The reference keeps accum_rec per channel and forms
+    // sum_c (c_c - accum_c) dL/dpix_c; the same quantity with the dot products taken first:
+    //   cd_i = sum_c colour_c(i) dL/dpix_c + depth(i) dL/dpix_depth,   A <- last_alpha * last_cd + (1 - last_alpha) * A,
+    //   dL/dalpha = cd_i - A
+    float A = 0.f, last_alpha = 0.f, last_cd = 0.f;
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
-    const int my_slot = reduce10_slot(lane);
-    float* const my_grad = a.grad_rec + (my_slot >= 0 ? my_slot : 0);
+    int ns = 0;   // filled survivor slots (warp-uniform)
 
-    // slot t of batch b holds list index m-1-(b*CB+t)
+    // slot t of batch b holds list index m-1-(b*BCB+t); threads >= BCB only composite
     uint32_t id_next = 0;
     {
         const int i0 = m - 1 - tid;
-        if (i0 >= 0) {
+        if (tid < BCB && i0 >= 0) {
             const uint32_t id = a.point_list[range.x + i0];
-            s_id[0][tid] = id;
-            cp_async16(&s_rec[0][tid].a, &a.xyAB[id]);
-            cp_async16(&s_rec[0][tid].b, &a.Cod[id]);
-            cp_async16(&s_rec[0][tid].c, &a.rgb[id]);
+            cp_async16(&sm.rec[0][tid].a, &a.xyAB[id]);
+            cp_async16(&sm.rec[0][tid].b, &a.Cod[id]);
+            cp_async16(&sm.rec[0][tid].c, &a.rgb[id]);
         }
         cp_async_commit();
-        const int i1 = m - 1 - (CB + tid);
-        if (i1 >= 0) id_next = a.point_list[range.x + i1];
+        const int i1 = m - 1 - (BCB + tid);
+        if (tid < BCB && i1 >= 0) id_next = a.point_list[range.x + i1];
         cp_async_wait_all();
         __syncthreads();
     }
 
     for (int b = 0; b < nb; ++b) {
         const int buf = b & 1;
-        {
-            const int i1 = m - 1 - ((b + 1) * CB + tid);
+        if (tid < BCB) {
+            const int i1 = m - 1 - ((b + 1) * BCB + tid);
             if (i1 >= 0) {
-                s_id[buf ^ 1][tid] = id_next;
-                cp_async16(&s_rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
-                cp_async16(&s_rec[buf ^ 1][tid].b, &a.Cod[id_next]);
-                cp_async16(&s_rec[buf ^ 1][tid].c, &a.rgb[id_next]);
+                cp_async16(&sm.rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
+                cp_async16(&sm.rec[buf ^ 1][tid].b, &a.Cod[id_next]);
+                cp_async16(&sm.rec[buf ^ 1][tid].c, &a.rgb[id_next]);
             }
-            cp_async_commit();
-            const int i2 = m - 1 - ((b + 2) * CB + tid);
+            const int i2 = m - 1 - ((b + 2) * BCB + tid);
             if (i2 >= 0) id_next = a.point_list[range.x + i2];
         }
-        const int top = m - 1 - b * CB;           // list index of slot 0
-        const int cnt = min(CB, top + 1);
-        const Rec* rec = s_rec[buf];
+        cp_async_commit();
+        const int top = m - 1 - b * BCB;           // list index of slot 0
+        const int cnt = min(BCB, top + 1);
+        const Rec* rec = sm.rec[buf];
         // the warp has nothing to do for instances at or above warp_max
         if (top - (cnt - 1) < warp_max) {
             for (int c0 = 0; c0 < cnt; c0 += 32) {
-                const int j = c0 + lane;
+                const int jc = c0 + lane;
                 bool pass = false;
-                if (j < cnt && top - j < warp_max) {
-                    const float4 g0 = rec[j].a;
-                    const float4 g1 = rec[j].b;
+                if (jc < cnt && top - jc < warp_max) {
+                    const float4 g0 = rec[jc].a;
+                    const float4 g1 = rec[jc].b;
                     const float q = rect_min_q(g0.z, g0.w, g1.x, g0.x - rx1, g0.x - rx0,
                                                g0.y - ry1, g0.y - ry0);
-                    pass = !(q > g1.w);
+                    pass = !(q > g1.z);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, pass);
                 while (mask) {
@@ -375,49 +415,40 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
                     const bool contrib = contributor < last_contributor && !(power > 0.0f) &&
                                          !(alpha < 1.0f / 255.0f);
                     if (!__any_sync(0xffffffffu, contrib)) continue;
-                    float v[10];
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) v[i] = 0.f;
+                    float X = 0.f, w = 0.f;
                     if (contrib) {
                         const float4 col = r.c;
                         // 1/(1-alpha): alpha <= 0.99, approx reciprocal (1 ulp) instead of
                         // the two IEEE divisions of backward.cu:529,567
                         const float inv = rcp_approx(1.f - alpha);
                         T = T * inv;
-                        const float w = alpha * T;
-                        const float om = 1.f - last_alpha;
-                        acc0 = last_alpha * lc0 + om * acc0;
-                        acc1 = last_alpha * lc1 + om * acc1;
-                        acc2 = last_alpha * lc2 + om * acc2;
-                        accd = last_alpha * last_depth + om * accd;
-                        lc0 = col.x; lc1 = col.y; lc2 = col.z; last_depth = g1.z;
-                        float dL_dalpha = (col.x - acc0) * dpix0 + (col.y - acc1) * dpix1 +
-                                          (col.z - acc2) * dpix2 + (g1.z - accd) * dpixd;
-                        v[6] = w * dpix0;
-                        v[7] = w * dpix1;
-                        v[8] = w * dpix2;
-                        v[9] = w * dpixd;
-                        dL_dalpha = dL_dalpha * T + nbg * inv;
+                        w = alpha * T;
+                        A = last_alpha * last_cd + (1.f - last_alpha) * A;
+                        const float cdv = col.x * dpix0 + col.y * dpix1 + col.z * dpix2 + col.w * dpixd;
+                        last_cd = cdv;
                         last_alpha = alpha;
-                        const float dL_dG = g1.y * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-                        const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-                        const float h = -0.5f * dL_dG;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = h * gdx * dx;
-                        v[3] = h * gdx * dy;
-                        v[4] = h * gdy * dy;
-                        v[5] = G * dL_dalpha;
+                        X = G * ((cdv - A) * T + nbg * inv);
                     }
-                    const float sum = warp_reduce10(v, lane);
-                    if (my_slot >= 0) atomicAdd(my_grad + (size_t)s_id[buf][jj] * GRAD_REC, sum);
+                    sm.xw[warp][ns][lane] = make_float2(X, w);
+                    if (lane == 0) {
+                        sm.slot_a[warp][ns] = g0;
+                        sm.slot_b[warp][ns] = g1;
+                    }
+                    if (++ns == BKS) {
+                        __syncwarp();
+                        bwd_flush(sm, warp, lane, BKS, cx, cy, ddelx_dx, ddely_dy, a.grad_rec);
+                        __syncwarp();
+                        ns = 0;
+                    }
                 }
             }
         }
         cp_async_wait_all();
         __syncthreads();
+    }
+    if (ns) {
+        __syncwarp();
+        bwd_flush(sm, warp, lane, ns, cx, cy, ddelx_dx, ddely_dy, a.grad_rec);
     }
 }
 

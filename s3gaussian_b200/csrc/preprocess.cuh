@@ -373,9 +373,12 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(PreFwdA
     a.radii[idx] = (int)po.radius;
     a.depth_key[idx] = __float_as_uint(po.depth);
     a.xyAB[idx] = make_float4(po.pix.x, po.pix.y, po.conic.x, po.conic.y);
-    a.Cod[idx] = make_float4(po.conic.z, opacity, po.depth,
-                             cull_tau(opacity, po.conic.x, po.conic.y, po.conic.z, po.lam_max, po.lam_min));
-    a.rgb[idx] = make_float4(col.x, col.y, col.z, 0.f);
+    // Cod.w carries the Gaussian's own index: the backward composite takes the target of its REDs from the
+    // staged record instead of a second id table
+    a.Cod[idx] = make_float4(po.conic.z, opacity,
+                             cull_tau(opacity, po.conic.x, po.conic.y, po.conic.z, po.lam_max, po.lam_min),
+                             __uint_as_float((uint32_t)idx));
+    a.rgb[idx] = make_float4(col.x, col.y, col.z, po.depth);
     a.rect[idx] = make_ushort4((unsigned short)po.rminx, (unsigned short)po.rminy, (unsigned short)po.rmaxx,
                                (unsigned short)po.rmaxy);
     a.tiles_touched[idx] = (po.rmaxy - po.rminy) * (po.rmaxx - po.rminx);

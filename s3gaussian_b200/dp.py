@@ -89,18 +89,20 @@ class GradBucket:
         return self.flat
 
 
-def sync_densify_stats(xyz_gradient_accum, denom, max_radii2D, visibility=None):
-    """Make the densification statistics identical on every rank (train.py:489-499):
-    the gradient-norm accumulator and its denominator add up, the screen radii take the max."""
+def sync_view_stats(viewspace_grad: torch.Tensor, radii: torch.Tensor):
+    """The batch statistics of ONE training step, combined over the ranks' views exactly as the reference
+    combines the views of its sequential batch loop: the screen-space gradients ADD
+    (train.py:435-437: viewspace_point_tensor_grad += viewspace_point_tensor_list[idx].grad) and the radii take
+    the MAX (train.py:391 `radii = torch.cat(radii_list,0).max(dim=0).values`), so `radii > 0` is the OR of the
+    per-view visibility filters (:392).  Call it ONCE per step on the local per-step tensors (in place), then
+    make ONE `GaussianModel.densification_step(viewspace_grad, radii)` call on every rank: the accumulators
+    `xyz_gradient_accum` / `denom` / `max_radii2D` themselves are never all-reduced (they would be re-summed
+    every step)."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):
-        return
-    dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM)
-    dist.all_reduce(denom, op=dist.ReduceOp.SUM)
-    dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX)
-    if visibility is not None:
-        v = visibility.to(torch.int32)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        visibility.copy_(v.bool())
+        return viewspace_grad, radii
+    dist.all_reduce(viewspace_grad, op=dist.ReduceOp.SUM)
+    dist.all_reduce(radii, op=dist.ReduceOp.MAX)
+    return viewspace_grad, radii
 
 
 def broadcast_gaussians(tensors: dict, src: int = 0) -> dict:

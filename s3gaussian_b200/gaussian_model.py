@@ -241,15 +241,43 @@ class GaussianModel:
                                                      max_steps=training_args.position_lr_max_steps)
 
     def update_learning_rate(self, iteration):
-        """gaussian_model.py:203-215 as written upstream: the xyz and grid groups follow their schedules; the
-        'deformation' group's schedule is evaluated but not assigned (the elif branch only computes lr)."""
+        """gaussian_model.py:203-218: the xyz, grid and deformation groups follow their exponential schedules;
+        returns the xyz learning rate (train.py:321)."""
+        lr_pos = None
         for group in self.optimizer.param_groups:
             if group["name"] == "xyz":
-                group["lr"] = self.xyz_scheduler_args(iteration)
+                lr_pos = group["lr"] = self.xyz_scheduler_args(iteration)
             if "grid" in group["name"]:
                 group["lr"] = self.grid_scheduler_args(iteration)
             elif group["name"] == "deformation":
-                self.deformation_scheduler_args(iteration)
+                group["lr"] = self.deformation_scheduler_args(iteration)
+        return lr_pos
+
+    # ---- checkpoints (gaussian_model.py:71-111; written by train.py:231,531, read by train.py:617) -------
+    def capture(self):
+        """The reference's 14-tuple, same order, so torch.save((gaussians.capture(), iteration), path) files are
+        interchangeable with the reference's."""
+        return (self.active_sh_degree, self._xyz, self._deformation.state_dict(), self._deformation_table,
+                self._features_dc, self._features_rest, self._scaling, self._rotation, self._opacity, self.max_radii2D,
+                self.xyz_gradient_accum, self.denom, self.optimizer.state_dict(), self.spatial_lr_scale)
+
+    def restore(self, model_args, training_args):
+        """gaussian_model.py:89-111.  Accepts a tuple captured by the reference class (its optimizer state dict is
+        torch.optim.Adam's, which FusedAdam shares) or by this one."""
+        (self.active_sh_degree, xyz, deform_state, table, f_dc, f_rest, scaling, rotation, opacity, max_radii2D,
+         xyz_gradient_accum, denom, opt_dict, self.spatial_lr_scale) = model_args
+        dev = xyz.device if xyz.is_cuda else torch.device("cuda")
+        mk = lambda t: nn.Parameter(t.detach().to(dev).float().contiguous().requires_grad_(True))
+        self._xyz, self._features_dc, self._features_rest = mk(xyz), mk(f_dc), mk(f_rest)
+        self._scaling, self._rotation, self._opacity = mk(scaling), mk(rotation), mk(opacity)
+        self._deformation_table = table.to(dev)
+        self.max_radii2D = max_radii2D.to(dev)
+        self._deformation = self._deformation.to(dev)
+        self._deformation.load_state_dict(deform_state)
+        self.training_setup(training_args)
+        self.xyz_gradient_accum = xyz_gradient_accum.to(dev)
+        self.denom = denom.to(dev)
+        self.optimizer.load_state_dict(opt_dict)
 
     # ---- per-iteration statistics (train.py:489-491, gaussian_model.py:693-695) --------------------
     def add_densification_stats(self, viewspace_point_tensor, update_filter):
@@ -281,6 +309,8 @@ class GaussianModel:
             src = src.contiguous()
             rf = math.prod(src.shape[1:])
             dst = torch.empty((n_out, *src.shape[1:]), device=dev, dtype=torch.float32)
+            if rf == 0:      # zero-width rows (_features_rest at max_sh_degree == 0): nothing to gather
+                return dst
             descs.append(_lib.RowTensor(src.data_ptr(), dst.data_ptr(), int(rf), 1 if zero_new else 0))
             hold.append(src)
             return dst

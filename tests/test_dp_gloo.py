@@ -47,10 +47,17 @@ def _worker(rank, world, port, results):
     bucket.all_reduce()
     results[f"flat{rank}"] = bucket.flat.clone()
     # densify statistics
-    acc = torch.full((5, 1), float(rank + 1)); den = torch.ones(5, 1); rad = torch.tensor([1.0 + rank, 5.0 - rank])
-    vis = torch.tensor([rank == 0, False, rank == 1])
-    dp.sync_densify_stats(acc, den, rad, vis)
-    results[f"stats{rank}"] = (acc.clone(), den.clone(), rad.clone(), vis.clone())
+    # per-step densify statistics: two steps, each reduced once (train.py:391-392,435-437,489-491)
+    acc, den, maxr = torch.zeros(3, 1), torch.zeros(3, 1), torch.zeros(3)
+    for step in range(2):
+        vgrad = torch.tensor([[3.0, 4.0, 0.0], [0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]) * (rank + 1 + step)
+        radii = torch.tensor([2 + rank, 0, 5 * rank + step], dtype=torch.int32)
+        dp.sync_view_stats(vgrad, radii)
+        vis = radii > 0                                     # what densification_step does on the device
+        maxr[vis] = torch.max(maxr[vis], radii[vis].float())
+        acc[vis] += torch.norm(vgrad[vis, :2], dim=-1, keepdim=True)
+        den[vis] += 1
+    results[f"stats{rank}"] = (acc.clone(), den.clone(), maxr.clone())
     # densify on rank 0 changes the point count; everyone must end up with rank 0's tensors
     tensors = {"xyz": torch.arange(21.0).view(7, 3) if rank == 0 else torch.zeros(5, 3),
                "opacity": torch.arange(7.0).view(7, 1) if rank == 0 else torch.zeros(5, 1)}
@@ -74,9 +81,12 @@ def test_view_parallel_step_equals_sequential_batch():
                      params[2].grad.permute(0, 2, 3, 1).reshape(-1)])     # channels-last memory order
     for r in range(world):
         assert torch.allclose(results[f"flat{r}"], ref, rtol=1e-5, atol=1e-6)
-        acc, den, rad, vis = results[f"stats{r}"]
-        assert torch.equal(acc, torch.full((5, 1), 3.0)) and torch.equal(den, torch.full((5, 1), 2.0))
-        assert torch.equal(rad, torch.tensor([2.0, 5.0])) and vis.tolist() == [True, False, True]
+        acc, den, maxr = results[f"stats{r}"]
+        # step 0: grads x(1+2)=3, radii max (3, 0, 5); step 1: grads x(2+3)=5, radii (3, 0, 6): norm of the SUMMED
+        # gradient once per step and +1 in denom per step - not the sum of per-view norms / visibility counts
+        assert torch.allclose(acc, torch.tensor([[5.0 * 3 + 5.0 * 5], [0.0], [3.0 + 5.0]]))
+        assert torch.equal(den, torch.tensor([[2.0], [0.0], [2.0]]))
+        assert torch.equal(maxr, torch.tensor([3.0, 0.0, 6.0]))
         assert torch.equal(results[f"bc{r}"]["xyz"], torch.arange(21.0).view(7, 3))
         assert results[f"bc{r}"]["opacity"].shape == (7, 1)
         assert results[f"t{r}"] == 4.0

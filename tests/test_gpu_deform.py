@@ -160,9 +160,11 @@ def test_render_coarse_stage_and_override_color(built_lib, oracle_lib):
         assert k in out3
 
 
-def test_render_matches_reference_stack_on_gpu(built_lib):
+@pytest.mark.parametrize("P,W,H", [(200_000, 960, 640), (500_000, 1920, 1280)], ids=["200k_960x640", "config3_500k_1920x1280"])
+def test_render_matches_reference_stack_on_gpu(P, W, H, built_lib):
     """Same parameters through the REFERENCE stack on this GPU: its PyTorch deform_network + activations +
-    eval_sh + its CUDA rasterizer (the code path of gaussian_renderer/__init__.py:89-166)."""
+    eval_sh + its CUDA rasterizer (the code path of gaussian_renderer/__init__.py:89-166).  The second case is
+    BASELINE config 3 at its real size (500k Gaussians, fine stage, 1920x1280, rgb + feat passes)."""
     if not (ref_ext.available() and ref_ext.deform_available()):
         pytest.skip("oracle/_ref not present")
     from s3gaussian_b200 import synthetic as syn
@@ -170,7 +172,6 @@ def test_render_matches_reference_stack_on_gpu(built_lib):
     from s3gaussian_b200.gaussian_renderer import render, PipelineParams, GaussianModelLite
     ref = ref_ext.load()
     ref_deform_network, eval_sh = ref_ext.load_ref_deform()
-    P, W, H = 200_000, 960, 640
     cloud = syn.make_cloud(P, seed=0, width=W, height=H)
     cam = syn.make_camera(W, H, (0, 0, 2.0), time=0.37)
     st = syn.make_deform_state(0, weight_scale=0.2)

@@ -58,7 +58,7 @@ def test_cuda_matches_reference_golden(path, ours):
     np.testing.assert_array_equal(views["xyAB"][vis, :2].view(np.uint32), z["means2D"][vis].view(np.uint32))
     conic = np.stack([views["xyAB"][:, 2], views["xyAB"][:, 3], views["Cod"][:, 0], views["Cod"][:, 1]], 1)
     np.testing.assert_array_equal(conic[vis].view(np.uint32), z["conic_opacity"][vis].view(np.uint32))
-    np.testing.assert_array_equal(views["Cod"][vis, 2].view(np.uint32), z["depths"][vis].view(np.uint32))
+    np.testing.assert_array_equal(views["rgb"][vis, 3].view(np.uint32), z["depths"][vis].view(np.uint32))
     assert util.relerr(color.cpu().numpy(), z["color"]) < TOL
     assert util.relerr(depth.cpu().numpy(), z["depth"]) < TOL
     assert util.relerr(views["final_T"], z["final_T"]) < TOL
@@ -109,25 +109,48 @@ def _need_ref():
     return ref_ext.load()
 
 
-@pytest.mark.parametrize("P,W,H,mode", [(100_000, 960, 640, "sh"), (100_000, 960, 640, "rgb"),
-                                        (500_000, 1920, 1280, "rgb"), (2_000_000, 1920, 1280, "sh")])
-def test_cuda_matches_reference_extension_at_benchmark_sizes(P, W, H, mode, ours):
-    """BASELINE configs 2-4 geometry: identical Gaussians + camera through both
-    implementations; integer state bit-exact, floats within 1e-4."""
+def bench_camera(W, H, rank=0):
+    """the camera bench.py times on `rank` (bench.py: ring[1 + 3 * ((rank * 6) % 50)])"""
+    from s3gaussian_b200 import synthetic as syn
+    return syn.waymo_ring(W, H, frames=50)[1 + 3 * ((rank * 6) % 50)]
+
+
+@pytest.mark.parametrize("P,W,H,mode,view", [(100_000, 960, 640, "sh", "front"), (100_000, 960, 640, "rgb", "front"),
+                                             (500_000, 1920, 1280, "rgb", "front"), (500_000, 1920, 1280, "sh", "bench"),
+                                             (2_000_000, 1920, 1280, "sh", "front"),
+                                             (2_000_000, 1920, 1280, "sh", "bench")])
+def test_cuda_matches_reference_extension_at_benchmark_sizes(P, W, H, mode, view, ours):
+    """BASELINE configs 2-4 geometry: identical Gaussians + camera through both implementations; integer state
+    bit-exact, floats within 1e-4 of the tensor max AND element-wise within 1e-4 relative + a stated absolute
+    floor.  view "bench" is the exact camera of the default bench.py line (waymo_ring[1])."""
     from s3gaussian_b200 import synthetic as syn
     ref = _need_ref()
     cloud = syn.make_cloud(P, seed=0)
-    cam = syn.make_camera(W, H, (0, 0, 2.0))
+    cam = syn.make_camera(W, H, (0, 0, 2.0)) if view == "front" else bench_camera(W, H, 0)
     d = util.scene_inputs(cloud, cam, mode=mode, sh_degree=3, bg=(0.0, 0.0, 0.0))
     gc, gd = util.seeded_grads(d, 7)
     r = util.run_module(ref, d, DEV, gc, gd)
+    r2 = util.run_module(ref, d, DEV, gc, gd)       # the reference's own run-to-run spread (unordered atomics)
     m = util.run_module(ours, d, DEV, gc, gd)
     assert torch.equal(r["radii"], m["radii"])
     assert util.relerr(m["color"].cpu().numpy(), r["color"].cpu().numpy()) < TOL
     assert util.relerr(m["depth"].cpu().numpy(), r["depth"].cpu().numpy()) < TOL
+    # forward images element-wise: 1e-4 relative + 1e-6 absolute (colours are O(1), depths O(10))
+    for k in ("color", "depth"):
+        frac, worst, _ = util.elementwise(m[k].cpu().numpy(), r[k].cpu().numpy(), 1e-4, 1e-6)
+        assert frac == 0.0, (k, frac, worst)
     for k in r["grads"]:
-        e = util.relerr(m["grads"][k].cpu().numpy(), r["grads"][k].cpu().numpy())
+        a, b, b2 = m["grads"][k].cpu().numpy(), r["grads"][k].cpu().numpy(), r2["grads"][k].cpu().numpy()
+        e = util.relerr(a, b)
         assert e < TOL, (k, e)
+        # element-wise: |ours - ref| <= 1e-4 |ref| + atol, atol = max(4 x the reference's own run-to-run spread
+        # on this input, 1e-6 of the tensor max)
+        atol = util.grad_atol(b, b2)
+        frac, worst, idx = util.elementwise(a, b, 1e-4, atol)
+        print(f"[elementwise] P={P} {mode} {view} {k}: max-normalised {e:.2e}, atol {atol:.2e} "
+              f"(ref spread {float(np.abs(b - b2).max()):.2e}, tensor max {float(np.abs(b).max()):.2e}), "
+              f"outside {frac:.2e}, worst ratio {worst:.2f}")
+        assert frac <= 1e-6, (k, frac, worst, idx)
     # internal state bit for bit
     E = torch.Tensor([])
     g = lambda k: d[k].to(DEV).contiguous() if d[k] is not None else E
@@ -144,6 +167,35 @@ def test_cuda_matches_reference_extension_at_benchmark_sizes(P, W, H, mode, ours
                                          tiles_touched=rg["tiles_touched"], point_list=rb["point_list"],
                                          keys=rb["point_list_keys"], ranges=ri["ranges"].reshape(-1, 2)[:tiles],
                                          n_contrib=ri["n_contrib"]))
+
+
+def test_scale_run_cameras_integer_state_matches_reference(ours):
+    """The 7 other cameras of the 1->8 GPU scaling run (rank r renders ring[1 + 3*((6r) % 50)]), 2M Gaussians,
+    1920x1280: radii, num_rendered, sorted point_list, tile keys, ranges and n_contrib bit-exact against the
+    reference extension, images within 1e-4."""
+    from s3gaussian_b200 import synthetic as syn
+    ref = _need_ref()
+    P, W, H = 2_000_000, 1920, 1280
+    cloud = syn.make_cloud(P, seed=0)
+    E = torch.Tensor([])
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    for rank in range(1, 8):
+        d = util.scene_inputs(cloud, bench_camera(W, H, rank), mode="sh", sh_degree=3, bg=(0.0, 0.0, 0.0))
+        g = lambda k: d[k].to(DEV).contiguous() if d[k] is not None else E
+        R0, rc, rdep, rrad, gb, bb, ib = ref._C.rasterize_gaussians(
+            d["bg"].to(DEV), g("means3D"), g("colors_precomp"), g("opacities"), g("scales"), g("rotations"), 1.0,
+            g("cov3D_precomp"), d["viewmatrix"].to(DEV), d["projmatrix"].to(DEV), d["tanfovx"], d["tanfovy"], H, W,
+            g("shs"), 3, d["campos"].to(DEV), False, False)
+        torch.cuda.synchronize()
+        rg, rb, ri = ref_ext.decode_geom(gb, P), ref_ext.decode_binning(bb, R0), ref_ext.decode_image(ib, W * H)
+        del gb, bb, ib
+        color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+        check_state_vs(views, radii, R, dict(num_rendered=R0, radii=rrad.cpu().numpy(),
+                                             tiles_touched=rg["tiles_touched"], point_list=rb["point_list"],
+                                             keys=rb["point_list_keys"], ranges=ri["ranges"].reshape(-1, 2)[:tiles],
+                                             n_contrib=ri["n_contrib"]))
+        assert util.relerr(color.cpu().numpy(), rc.cpu().numpy()) < TOL, rank
+        assert util.relerr(depth.cpu().numpy(), rdep.cpu().numpy()) < TOL, rank
 
 
 def test_mark_visible_matches_reference_and_oracle(ours, oracle_lib):
@@ -257,7 +309,7 @@ def test_full_size_properties(ours):
     assert int(tt.astype(np.int64).sum()) == R                       # checksum of counts
     assert np.array_equal((tt > 0), radii.cpu().numpy() > 0)
     assert np.all(np.diff(plt.astype(np.int64)) >= 0)                 # sorted by tile
-    depth_bits = v["Cod"][:, 2].view(np.uint32)[pl].astype(np.int64)
+    depth_bits = v["rgb"][:, 3].view(np.uint32)[pl].astype(np.int64)
     key = (plt.astype(np.int64) << 32) | depth_bits
     assert np.all(np.diff(key) >= 0)                                  # then by depth bits
     ties = np.diff(key) == 0

@@ -385,3 +385,105 @@ def test_training_loop_with_model_render_loss_and_densify(built_lib):
         last[cam] = loss.item()
     assert all(last[c] < first[c] for c in first), (first, last)
     assert len(sizes) > 1
+
+
+# ---- checkpoints: the reference's capture() tuple (scene/gaussian_model.py:71-111) ----------------------------
+def test_capture_restore_round_trip_with_reference_tuple(built_lib, tmp_path):
+    """A checkpoint written the way train.py:531 does - torch.save((gaussians.capture(), iteration)) - by the
+    REFERENCE's own capture()/training_setup() method bodies (ast-extracted from oracle/_ref, reference
+    deform_network, torch.optim.Adam with two real steps) restores into our GaussianModel bit for bit, trains on,
+    and our capture() restores into the reference's restore()."""
+    import ast
+    import os
+    import ref_ext
+    if not (ref_ext.gaussian_model_available() and ref_ext.deform_available()):
+        pytest.skip("oracle/_ref/s3g_ref not present (run oracle/build_ref.sh)")
+    from s3gaussian_b200 import synthetic as syn
+    from s3gaussian_b200.deformation import deform_network
+    from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params
+    base = os.path.join(ref_ext.REF_DIR, "s3g_ref")
+    ns = {"torch": torch, "nn": torch.nn, "np": np}
+    for path, names in ((os.path.join(base, "utils", "general_utils.py"), {"get_expon_lr_func"}),
+                        (os.path.join(base, "scene", "gaussian_model.py"),
+                         {"capture", "restore", "training_setup", "get_xyz"})):
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+
+    class Ref:
+        get_xyz = property(ns["get_xyz"])
+        capture, restore, training_setup = ns["capture"], ns["restore"], ns["training_setup"]
+    ref_dn, _ = ref_ext.load_ref_deform()
+    res, mres = (16, 12, 10, 7), (1, 2)
+    args = ref_ext.ref_deform_args(res, mres)
+    st = syn.make_deform_state(3, res, mres, aabb=((9.0, 4.0, 3.0), (-2.0, -4.0, -3.0)), weight_scale=0.2)
+    P = 3000
+    g = torch.Generator(device=DEV).manual_seed(5)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    ref = Ref()
+    ref._deformation = ref_dn(args).to(DEV)
+    ref._deformation.load_state_dict(st, strict=False)
+    mk = lambda t: torch.nn.Parameter(t.requires_grad_(True))
+    ref._xyz, ref._features_dc, ref._features_rest = mk(r(P, 3)), mk(r(P, 1, 3)), mk(r(P, 15, 3))
+    ref._scaling, ref._rotation, ref._opacity = mk(r(P, 3)), mk(r(P, 4)), mk(r(P, 1))
+    ref.active_sh_degree, ref.spatial_lr_scale = 2, 1.7
+    ref._deformation_table = torch.ones(P, dtype=torch.bool, device=DEV)
+    ref.max_radii2D = torch.rand(P, device=DEV, generator=g) * 30
+    opt_args = default_optimization_params()
+    ref.training_setup(opt_args)
+    ref.xyz_gradient_accum = torch.rand(P, 1, device=DEV, generator=g)
+    ref.denom = torch.randint(0, 5, (P, 1), device=DEV, generator=g).float()
+    for _ in range(2):
+        for grp in ref.optimizer.param_groups:
+            for p in grp["params"]:
+                p.grad = torch.randn(p.shape, device=DEV, generator=g) * 0.01
+        ref.optimizer.step()
+    path = str(tmp_path / "chkpnt_ref.pth")
+    torch.save((ref.capture(), 1234), path)
+
+    # ---- the reference checkpoint into our model ----
+    model_args, it = torch.load(path, weights_only=False)
+    assert it == 1234 and len(model_args) == 14
+    ours = GaussianModel(3, deformation=deform_network(args))
+    ours.restore(model_args, opt_args)
+    assert ours.active_sh_degree == 2 and ours.spatial_lr_scale == 1.7
+    for a in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity", "max_radii2D",
+              "xyz_gradient_accum", "denom", "_deformation_table"):
+        assert torch.equal(getattr(ours, a).detach(), getattr(ref, a).detach()), a
+    sd_o, sd_r = ours._deformation.state_dict(), ref._deformation.state_dict()
+    assert set(sd_o) == set(sd_r)
+    for k in sd_r:
+        assert torch.equal(sd_o[k].to(DEV), sd_r[k]), k
+    go, gr = ours.optimizer.param_groups, ref.optimizer.param_groups
+    assert [x["name"] for x in go] == [x["name"] for x in gr]
+    for a, b in zip(go, gr):
+        assert a["lr"] == b["lr"] and len(a["params"]) == len(b["params"])
+        for pa, pb in zip(a["params"], b["params"]):
+            sa, sb = ours.optimizer.state[pa], ref.optimizer.state[pb]
+            assert float(sa["step"]) == float(sb["step"]) == 2.0
+            assert torch.equal(sa["exp_avg"].reshape(-1), sb["exp_avg"].reshape(-1)) or \
+                torch.equal(sa["exp_avg"], sb["exp_avg"])
+            assert torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])
+    # training resumes identically: one more step with the same gradients on both sides
+    for a, b in zip(go, gr):
+        for pa, pb in zip(a["params"], b["params"]):
+            gt = torch.randn(pb.shape, device=DEV, generator=g) * 0.01
+            pa.grad, pb.grad = gt.clone(), gt.clone()
+    ours.optimizer.step()
+    ref.optimizer.step()
+    for a, b in zip(go, gr):
+        for pa, pb in zip(a["params"], b["params"]):
+            assert rel(pa, pb) < 2e-6, a["name"]
+
+    # ---- our checkpoint into the reference's restore() ----
+    path2 = str(tmp_path / "chkpnt_ours.pth")
+    torch.save((ours.capture(), 1235), path2)
+    model_args2, _ = torch.load(path2, weights_only=False)
+    ref2 = Ref()
+    ref2._deformation = ref_dn(args).to(DEV)
+    ref2.restore(model_args2, opt_args)
+    assert torch.equal(ref2._xyz.detach(), ours._xyz.detach()) and torch.equal(ref2.denom, ours.denom)
+    for a, b in zip(ref2.optimizer.param_groups, ours.optimizer.param_groups):
+        for pa, pb in zip(a["params"], b["params"]):
+            assert float(ref2.optimizer.state[pa]["step"]) == 3.0
+            assert torch.equal(ref2.optimizer.state[pa]["exp_avg_sq"], ours.optimizer.state[pb]["exp_avg_sq"])

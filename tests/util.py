@@ -131,6 +131,29 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
+def elementwise(a, b, rtol=1e-4, atol=0.0):
+    """Element-wise closeness |a-b| <= rtol*|b| + atol (north_star's "1e-4 relative fp32" read literally, plus an
+    absolute floor the caller states and justifies).  Returns (fraction of elements outside, worst excess ratio
+    |a-b| / (rtol*|b| + atol), index of the worst element)."""
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    lim = rtol * np.abs(b) + atol
+    err = np.abs(a - b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(lim > 0, err / lim, np.where(err > 0, np.inf, 0.0))
+    i = int(np.argmax(ratio)) if ratio.size else 0
+    return float((ratio > 1.0).mean()) if ratio.size else 0.0, float(ratio[i]) if ratio.size else 0.0, i
+
+
+def grad_atol(ref_run_a, ref_run_b, floor_of_max=1e-6):
+    """Absolute floor for element-wise gradient checks: the reference's OWN run-to-run spread on this input
+    (its backward accumulates with unordered fp32 atomics, backward.cu:550-587) times 4, but at least
+    `floor_of_max` of the tensor's largest magnitude (fp32 accumulation noise of a sum of hundreds of terms)."""
+    a = np.asarray(ref_run_a, np.float64)
+    b = np.asarray(ref_run_b, np.float64)
+    return max(4.0 * float(np.abs(a - b).max()), floor_of_max * float(np.abs(a).max()))
+
+
 def seeded_grads(d, seed=1):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(3, d["H"], d["W"], generator=g), torch.randn(1, d["H"], d["W"], generator=g))

@@ -137,7 +137,7 @@ def main():
     print("means2D bit mismatches (visible):", int((xyAB[vis, :2].view(np.uint32) != m2[vis].view(np.uint32)).sum()))
     ours_conic = np.stack([xyAB[:, 2], xyAB[:, 3], Cod[:, 0], Cod[:, 1]], 1)
     print("conic_opacity bit mismatches (visible):", int((ours_conic[vis].view(np.uint32) != co[vis].view(np.uint32)).sum()))
-    print("depth bit mismatches (visible):", int((Cod[vis, 2].view(np.uint32) != rg["depths"][vis].view(np.uint32)).sum()))
+    print("depth bit mismatches (visible):", int((rgb[vis, 3].view(np.uint32) != rg["depths"][vis].view(np.uint32)).sum()))
     rr = rg["rgb"].reshape(P, 3)
     print("rgb max abs diff (visible):", float(np.abs(rgb[vis, :3] - rr[vis]).max()), "bit mismatches:",
           int((rgb[vis, :3].view(np.uint32) != rr[vis].view(np.uint32)).sum()))

@@ -64,6 +64,10 @@ def parse():
     ap.add_argument("--no-train-iteration", action="store_true",
                     help="skip the whole-training-iteration leg (render + loss + stats + Adam, N == 1 only)")
     ap.add_argument("--cpu-sample", type=int, default=500_000)
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the BASELINE config 1-4 legs (bench_configs.py, N == 1 only)")
+    ap.add_argument("--configs", default="config1,config2,config3,config4",
+                    help="which of the extra config legs to run")
     return ap.parse_args()
 
 
@@ -419,6 +423,16 @@ def main():
         ms_train = timed(step_train, 10, 3)
         train_it = {"ms": round(ms_train / 10, 4), "iterations": 10, "what": what}
 
+    # ---- BASELINE configs 1-4 as extra keys (N == 1): same legs for both arms, see bench_configs.py ----
+    configs = None
+    if world == 1 and not a.no_extra_configs:
+        import bench_configs
+        del t, leaves, gc, gd
+        torch.cuda.empty_cache()
+        want = set(a.configs.split(","))
+        configs = bench_configs.run_all(a.impl, mod, dev, hbm,
+                                        skip=[c for c in ("config1", "config2", "config3", "config4") if c not in want])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -463,6 +477,8 @@ def main():
             out["cpu_baseline"] = cpu
     if train_it:
         out["train_iteration"] = train_it
+    if configs:
+        out["configs"] = configs
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

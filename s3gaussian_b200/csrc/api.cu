@@ -57,6 +57,53 @@ struct StageTimer {
 StageTimer g_timer;
 #define S3G_MARK(which, name) g_timer.mark(which, stream, name)
 
+// ---- the instance count as the host sees it ---------------------------------
+// Two words of mapped pinned memory per (thread, device): the scan kernel's last block stores {count, sequence}
+// there (st.volatile + __threadfence_system); the host polls the sequence word.  last_capacity is the binning
+// capacity (in instances) this thread requested on that device the last time.
+struct HostCount {
+    volatile uint64_t* host = nullptr;
+    volatile uint64_t* dev = nullptr;
+    uint64_t seq = 0;
+    int64_t last_capacity = 0;
+};
+HostCount* host_count() {
+    static thread_local HostCount table[64];
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+    HostCount* h = &table[d];
+    if (!h->host) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 2 * sizeof(uint64_t), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, p, 0) != cudaSuccess) return nullptr;
+        h->host = static_cast<volatile uint64_t*>(p);
+        h->dev = static_cast<volatile uint64_t*>(dp);
+        h->host[0] = 0;
+        h->host[1] = 0;
+    }
+    return h;
+}
+// Spin until the scan of call `seq` has published its total.  The stream is queried now and then so that a
+// faulted or finished-without-publishing stream ends the wait with an error instead of a hang.
+int wait_host_count(HostCount* hc, uint64_t seq, cudaStream_t stream, int64_t* out) {
+    for (uint64_t spins = 0;; ++spins) {
+        if (hc->host[1] == seq) break;
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(S3G_ERR_CUDA, "num_rendered wait", q);
+            if (q == cudaSuccess && hc->host[1] != seq)
+                return fail(S3G_ERR_STATE, "num_rendered wait: stream drained without publishing the count");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __sync_synchronize();
+    *out = (int64_t)hc->host[0];
+    return S3G_OK;
+}
+
 // number of key bits that cover every tile id (getHigherMsb, rasterizer_impl.cu:35-50)
 int tile_key_bits(uint32_t tiles) {
     int b = 0;
@@ -149,8 +196,7 @@ int s3g_state_field(int buffer, const char* name, int64_t P, int64_t R, int widt
         if (f == "grad_rec") return set(g.grad_rec, 4, (size_t)P * GRAD_REC);
     } else if (buffer == 1) {
         BinningState b = BinningState::carve(base, R);
-        if (f == "point_list") return set(b.point_list, 4, R);
-        if (f == "point_list_tiles") return set(b.point_list_tiles, 4, R);
+        if (f == "point_list") return set(b.point_list, 4, R);   // first field: independent of the capacity
     } else if (buffer == 2) {
         ImageState s = ImageState::carve(base, width, height);
         TileGrid tg = tile_grid(width, height);
@@ -248,8 +294,12 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     pa.radii = radii; pa.xyAB = geom.xyAB; pa.Cod = geom.Cod; pa.rgb = geom.rgb;
     pa.depth_key = geom.depth_key; pa.tiles_touched = geom.tiles_touched; pa.rect = geom.rect;
     pa.clamped = geom.clamped; pa.order = geom.order_a;
+    pa.depth_hist = geom.sort.hist;
     pa.grid_x = tg.x; pa.grid_y = tg.y;
     g_timer.begin(0);
+    // one memset for everything the chained scan and the depth sort expect zeroed (look-back words, tickets,
+    // digit histograms - the histograms are filled by the preprocess kernel)
+    S3G_CUDA(cudaMemsetAsync(geom.scan_status, 0, geom.zero_bytes, stream), "memset scan/sort state");
     S3G_MARK(0, "preprocess_forward");
     {
         const bool use_sh = colors_precomp == nullptr;
@@ -271,82 +321,104 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
 
     // ---- depth digits of the LSD sort, over Gaussians --------------------
     S3G_CUDA(radix_sort_pairs((uint32_t)P, geom.depth_key, geom.order_a, geom.key_b, geom.order_b,
-                              nullptr, geom.order_a, 0, 32, geom.sort, stream),
+                              nullptr, geom.order_a, 0, 32, geom.sort, stream, nullptr, /*hist_ready=*/true),
              "depth sort");
     S3G_STAGE("depth sort");
 
-    S3G_MARK(0, "scan+readback");
+    S3G_MARK(0, "scan");
     // ---- offsets in depth order + total ----------------------------------
+    // The total (num_rendered, rasterizer_impl.cu:281-282) stays on the device for the binning kernels and is
+    // ALSO stored by the scan's last block into mapped pinned memory: the host reads it without a copy, an event or
+    // a stream synchronisation, after the rest of the forward has been enqueued.
+    HostCount* hc = host_count();
+    if (!hc) return fail(S3G_ERR_CUDA, "forward: pinned count buffer");
+    const uint64_t seq = ++hc->seq;
     {
-        const size_t zb = (size_t)(reinterpret_cast<char*>(geom.scan_misc + 32) -
-                                   reinterpret_cast<char*>(geom.scan_status));
-        S3G_CUDA(cudaMemsetAsync(geom.scan_status, 0, zb, stream), "memset scan");
         const uint32_t nblk = (uint32_t)div_up64(P, SCAN_TILE);
         scan_tiles_kernel<<<nblk, SCAN_THREADS, 0, stream>>>(geom.order_a, geom.tiles_touched,
                                                              (uint32_t)P, geom.offsets,
-                                                             geom.scan_status, geom.scan_misc);
+                                                             geom.scan_status, geom.scan_misc, hc->dev, seq);
         S3G_STAGE("scan");
     }
-    // rasterizer_impl.cu:281-282: the one read-back that sizes the binning arena.  Pinned
-    // destination + event spin-wait: a blocking cudaStreamSynchronize() after a long queue
-    // sleeps in the OS and wakes up milliseconds late, which idles the GPU.
-    uint64_t total = 0;
-    {
-        static thread_local uint64_t* h_total = nullptr;
-        static thread_local cudaEvent_t ev = nullptr;
-        if (!h_total) {
-            S3G_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_total), sizeof(uint64_t), cudaHostAllocDefault),
-                     "pinned readback alloc");
-            S3G_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "readback event");
-        }
-        S3G_CUDA(cudaMemcpyAsync(h_total, geom.scan_misc + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream),
-                 "num_rendered copy");
-        S3G_CUDA(cudaEventRecord(ev, stream), "num_rendered event");
-        cudaError_t q;
-        while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
-        if (q != cudaSuccess) return fail(S3G_ERR_CUDA, "num_rendered wait", q);
-        total = *h_total;
+    const uint32_t* n_dev = geom.scan_misc + 2;     // low word of the u64 total (checked < 2^30 below)
+
+    // Capacity of the binning arena: what this thread asked for last time (the arena only grows).  The first call
+    // has nothing to go by and waits for the count; later calls enqueue everything against the remembered capacity
+    // and verify afterwards - the GPU never waits for the host.
+    int64_t cap = hc->last_capacity;
+    int64_t R = -1;
+    if (cap <= 0) {
+        int rc = wait_host_count(hc, seq, stream, &R);
+        if (rc != S3G_OK) return rc;
+        if (R >= (1ll << 30)) return fail(S3G_ERR_ARG, "forward: more than 2^30 tile instances");
+        cap = R + R / 8 + 1;
     }
-    if (total >= (1ull << 30)) return fail(S3G_ERR_ARG, "forward: more than 2^30 tile instances");
-    const int64_t R = (int64_t)total;
+    const uint32_t n_tiles = (uint32_t)tg.count();
+    const int tile_bits = tile_key_bits(n_tiles);
+    for (int attempt = 0;; ++attempt) {
+        char* bptr = binning_alloc(binning_user, s3g_binning_bytes(cap));
+        if (!bptr) return fail(S3G_ERR_ALLOC, "forward: binning allocator returned NULL");
+        hc->last_capacity = cap;
+        BinningState bin = BinningState::carve(bptr, cap);
 
-    char* bptr = binning_alloc(binning_user, s3g_binning_bytes(R));
-    if (!bptr) return fail(S3G_ERR_ALLOC, "forward: binning allocator returned NULL");
-    BinningState bin = BinningState::carve(bptr, R);
-
-    S3G_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)tg.count() * sizeof(uint2), stream),
-             "memset ranges");
-    S3G_MARK(0, "emit");
-    if (R > 0) {
-        emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
-            (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, bin.tile_a,
-            bin.idx_a);
+        S3G_MARK(0, "emit");
+        S3G_CUDA(cudaMemsetAsync(img.tile_hist, 0, (size_t)n_tiles * sizeof(uint32_t), stream), "memset tile_hist");
+        S3G_CUDA(radix_sort_prepare(bin.sort, stream), "memset tile sort state");
+        {
+            const size_t hist_smem = (size_t)n_tiles * sizeof(uint32_t);
+            const int blocks_needed = (P + 255) / 256;
+            if (hist_smem <= 64 * 1024) {
+                if (hist_smem > 48 * 1024)
+                    S3G_CUDA(cudaFuncSetAttribute(emit_instances_kernel<true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem),
+                             "emit smem attribute");
+                const int grid = std::min(blocks_needed, 148 * 4);
+                emit_instances_kernel<true><<<grid, 256, hist_smem, stream>>>(
+                    (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, n_tiles,
+                    (uint32_t)cap, bin.tile_a, bin.idx_a, img.tile_hist);
+            } else {
+                emit_instances_kernel<false><<<blocks_needed, 256, 0, stream>>>(
+                    (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, n_tiles,
+                    (uint32_t)cap, bin.tile_a, bin.idx_a, img.tile_hist);
+            }
+        }
         S3G_STAGE("emit");
+        S3G_MARK(0, "tile_offsets");
+        {
+            const int npass = (tile_bits + RADIX_BITS - 1) / RADIX_BITS;
+            tile_offsets_kernel<<<1, 1024, 0, stream>>>(n_tiles, img.tile_hist, img.ranges, npass, tile_bits,
+                                                        bin.sort.hist);
+        }
+        S3G_STAGE("tile offsets");
         S3G_MARK(0, "tile_sort");
-        S3G_CUDA(radix_sort_pairs((uint32_t)R, bin.tile_a, bin.idx_a, bin.tile_b, bin.idx_b,
-                                  bin.point_list_tiles, bin.point_list, 0,
-                                  tile_key_bits((uint32_t)tg.count()), bin.sort, stream),
+        S3G_CUDA(radix_sort_pairs((uint32_t)cap, bin.tile_a, bin.idx_a, bin.tile_b, bin.idx_b, nullptr,
+                                  bin.point_list, 0, tile_bits, bin.sort, stream, n_dev, /*hist_ready=*/true),
                  "tile sort");
         S3G_STAGE("tile sort");
-        S3G_MARK(0, "tile_ranges");
-        tile_ranges_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, stream>>>(
-            (uint32_t)R, bin.point_list_tiles, img.ranges);
-        S3G_STAGE("ranges");
-    }
 
-    S3G_MARK(0, "render_forward");
-    RenderFwdArgs ra;
-    ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
-    ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb; ra.bg = background;
-    ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
-    ra.out_color = out_color; ra.out_depth = out_depth;
-    render_forward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
-    S3G_STAGE("render_forward");
-    S3G_MARK(0, nullptr);
+        S3G_MARK(0, "render_forward");
+        RenderFwdArgs ra;
+        ra.ranges = img.ranges; ra.point_list = bin.point_list; ra.W = width; ra.H = height;
+        ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb; ra.bg = background;
+        ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
+        ra.out_color = out_color; ra.out_depth = out_depth;
+        render_forward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+        S3G_STAGE("render_forward");
+        S3G_MARK(0, nullptr);
+
+        if (R < 0) {
+            int rc = wait_host_count(hc, seq, stream, &R);
+            if (rc != S3G_OK) return rc;
+            if (R >= (1ll << 30)) return fail(S3G_ERR_ARG, "forward: more than 2^30 tile instances");
+        }
+        if (R <= cap) break;
+        // the count outgrew the remembered capacity: every write above was clamped to `cap`, nothing is lost
+        // but this attempt's tail; grow the arena and run the tail again
+        if (attempt > 0) return fail(S3G_ERR_STATE, "forward: binning capacity still too small after growing");
+        cap = R + R / 8 + 1;
+        g_timer.begin(0);   // stage timers describe the attempt that counts
+        S3G_MARK(0, "retry");
+    }
     return R;
 }
 

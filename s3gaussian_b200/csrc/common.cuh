@@ -84,8 +84,9 @@ struct GeomState {
     uint32_t* order_b;
     uint32_t* offsets;       // exclusive scan of tiles_touched in depth order
     uint64_t* scan_status;   // chained-scan look-back words
-    uint32_t* scan_misc;     // [0]=ticket, [1..2]=total (u64)
+    uint32_t* scan_misc;     // [0]=ticket, [2..3]=total (u64): the instance count, read on the device by the binning
     SortTemp sort;
+    size_t zero_bytes;       // scan_status .. end of sort temp: zeroed by ONE memset before preprocess
     __host__ static GeomState carve(char* base, int64_t P, size_t* total = nullptr) {
         Carver c(base);
         GeomState g;
@@ -105,15 +106,17 @@ struct GeomState {
         g.scan_status = c.take<uint64_t>((size_t)div_up64(P > 0 ? P : 1, 2048) + 1);
         g.scan_misc = c.take<uint32_t>(32);
         g.sort = SortTemp::carve(c, P);
+        g.zero_bytes = c.measuring ? 0 : (size_t)((c.abase + c.off) - reinterpret_cast<char*>(g.scan_status));
         if (total) *total = c.off + 128;
         return g;
     }
 };
 
-// Per-instance state (R-indexed).
+// Per-instance state, indexed by instance; carved for a CAPACITY >= num_rendered (the arena is sized before the
+// count is known on the host).  point_list comes first so that its address does not depend on the capacity:
+// it is the only field the backward pass reads.
 struct BinningState {
     uint32_t* point_list;        // sorted Gaussian ids (rasterizer_impl.cu:184)
-    uint32_t* point_list_tiles;  // sorted tile ids (the high 32 key bits of rasterizer_impl.cu:186)
     uint32_t* tile_a;            // scratch ping-pong
     uint32_t* idx_a;
     uint32_t* tile_b;
@@ -124,7 +127,6 @@ struct BinningState {
         BinningState b;
         size_t n = (size_t)(R > 0 ? R : 1);
         b.point_list = c.take<uint32_t>(n);
-        b.point_list_tiles = c.take<uint32_t>(n);
         b.tile_a = c.take<uint32_t>(n);
         b.idx_a = c.take<uint32_t>(n);
         b.tile_b = c.take<uint32_t>(n);
@@ -140,6 +142,7 @@ struct ImageState {
     float* final_T;        // accum_alpha (rasterizer_impl.cu:175)
     uint32_t* n_contrib;   // rasterizer_impl.cu:176
     uint2* ranges;         // per-tile [start,end) (rasterizer_impl.cu:177)
+    uint32_t* tile_hist;   // instances per tile (scratch of the forward)
     __host__ static ImageState carve(char* base, int W, int H, size_t* total = nullptr) {
         Carver c(base);
         ImageState s;
@@ -148,6 +151,7 @@ struct ImageState {
         s.final_T = c.take<float>(N);
         s.n_contrib = c.take<uint32_t>(N);
         s.ranges = c.take<uint2>(tiles);
+        s.tile_hist = c.take<uint32_t>(tiles);
         if (total) *total = c.off + 128;
         return s;
     }

@@ -69,9 +69,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 
 // The sort kernels and their host driver are compiled in their own translation unit (radix_sort.cu,
 // which defines S3G_RADIX_SORT_IMPL); everyone else sees the declaration only.
+// n: item count known on the host, or the capacity when `n_dev` (device word with the true count, clamped to n)
+// is given.  hist_ready: the caller zeroed the temp block (radix_sort_prepare) and a producer kernel already
+// wrote the digit histograms st.hist[pass][digit]; otherwise the driver zeroes and runs sort_histogram_kernel.
+cudaError_t radix_sort_prepare(const SortTemp& st, cudaStream_t stream);
 cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_tmp,
                              uint32_t* vals_tmp, uint32_t* keys_final, uint32_t* vals_final, int begin_bit,
-                             int end_bit, const SortTemp& st, cudaStream_t stream);
+                             int end_bit, const SortTemp& st, cudaStream_t stream,
+                             const uint32_t* n_dev = nullptr, bool hist_ready = false);
 
 #ifdef S3G_RADIX_SORT_IMPL
 // ---- histogram of every digit of every pass in one read of the keys -------
@@ -107,11 +112,11 @@ sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int begin_b
 // ---- one digit pass --------------------------------------------------------
 // grid: exactly ceil(n / SORT_TILE) blocks.  status: [nblk][RADIX] zeroed.
 template <bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)   // 64 registers: four 43 KB blocks per SM (ranking is a latency chain)
 sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                     int shift, uint32_t mask, const uint32_t* __restrict__ hist,
-                     uint32_t* status, uint32_t* ticket) {
+                     const uint32_t* __restrict__ n_dev, int shift, uint32_t mask,
+                     const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket) {
     __shared__ uint32_t s_wc[SORT_THREADS / 32][RADIX];
     __shared__ uint32_t s_keys[SORT_TILE];
     __shared__ uint32_t s_vals[SORT_TILE];
@@ -127,6 +132,8 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         (&s_wc[0][0])[i * SORT_THREADS + tid] = 0;
     __syncthreads();
     const uint32_t bid = s_bid;
+    if (n_dev) n = min(n, *n_dev);                       // count produced on the device; grid sized for the capacity
+    if (bid * (uint32_t)SORT_TILE >= n) return;          // nobody looks back at a block past the end
     const uint32_t base = bid * (uint32_t)SORT_TILE + warp * (SORT_ITEMS * 32);
 
     uint32_t k[SORT_ITEMS];
@@ -154,14 +161,6 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[i] = old + __popc(peers & lt);
         __syncwarp();
-    }
-    // the values are only needed for the scatter; fetching them here (not there) keeps the global round
-    // trip off the critical path behind the look-back
-    uint32_t v_in[SORT_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t idx = base + i * 32 + lane;
-        v_in[i] = idx < n ? vals_in[idx] : 0u;
     }
     __syncthreads();
     // digit tid: exclusive prefix over warps, block count
@@ -211,6 +210,14 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     s_gofs[tid] = hexcl + excl - dstart;
     __syncthreads();
 
+    // the values are only needed from here on (16 more live registers across the look-back cost a fourth
+    // resident block per SM)
+    uint32_t v_in[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        uint32_t idx = base + i * 32 + lane;
+        v_in[i] = idx < n ? vals_in[idx] : 0u;
+    }
     // scatter to the block-local digit-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -238,21 +245,29 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 // writes to (keys_final,vals_final) (keys_final may be NULL = don't care).
 // `st` must have been carved for >= n items.  Returns the cudaError of the
 // launches.
+cudaError_t radix_sort_prepare(const SortTemp& st, cudaStream_t stream) {
+    return cudaMemsetAsync(st.hist, 0, st.zero_bytes, stream);
+}
+
 cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
                                     uint32_t* keys_tmp, uint32_t* vals_tmp, uint32_t* keys_final,
                                     uint32_t* vals_final, int begin_bit, int end_bit,
-                                    const SortTemp& st, cudaStream_t stream) {
+                                    const SortTemp& st, cudaStream_t stream, const uint32_t* n_dev,
+                                    bool hist_ready) {
     if (n == 0) return cudaSuccess;
     int bits = end_bit - begin_bit;
     int npass = (bits + RADIX_BITS - 1) / RADIX_BITS;
     if (npass < 1) npass = 1;
     if (npass > SORT_MAX_PASSES) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(st.hist, 0, st.zero_bytes, stream);
-    if (e != cudaSuccess) return e;
     const uint32_t nblk = (uint32_t)div_up64(n, SORT_TILE);
-    uint32_t hgrid = nblk < 148u * 8u ? nblk : 148u * 8u;
-    sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, stream>>>(keys_in, n, begin_bit, end_bit, npass,
-                                                              st.hist);
+    if (!hist_ready) {
+        cudaError_t e = radix_sort_prepare(st, stream);
+        if (e != cudaSuccess) return e;
+        if (n_dev) return cudaErrorInvalidValue;       // a device-side count needs a producer-built histogram
+        uint32_t hgrid = nblk < 148u * 8u ? nblk : 148u * 8u;
+        sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, stream>>>(keys_in, n, begin_bit, end_bit, npass,
+                                                                  st.hist);
+    }
     uint32_t* src_k = keys_in;
     uint32_t* src_v = vals_in;
     for (int p = 0; p < npass; ++p) {
@@ -266,11 +281,11 @@ cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
         uint32_t* status = st.status + (size_t)p * nblk * RADIX;
         if (dst_k)
             sort_onesweep_kernel<true><<<nblk, SORT_THREADS, 0, stream>>>(
-                src_k, src_v, dst_k, dst_v, n, shift, mask, st.hist + p * RADIX, status,
+                src_k, src_v, dst_k, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status,
                 st.tickets + p);
         else
             sort_onesweep_kernel<false><<<nblk, SORT_THREADS, 0, stream>>>(
-                src_k, src_v, nullptr, dst_v, n, shift, mask, st.hist + p * RADIX, status,
+                src_k, src_v, nullptr, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status,
                 st.tickets + p);
         src_k = dst_k;
         src_v = dst_v;
@@ -290,7 +305,8 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
-                  uint32_t n, uint32_t* __restrict__ offsets, uint64_t* status, uint32_t* misc) {
+                  uint32_t n, uint32_t* __restrict__ offsets, uint64_t* status, uint32_t* misc,
+                  volatile uint64_t* host_total /*[2] mapped pinned: {total, sequence}*/, uint64_t seq) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_bid;
     __shared__ uint64_t s_prefix;
@@ -311,25 +327,47 @@ scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict
     }
     uint32_t block_total;
     uint32_t texcl = block_excl_scan_256(sum, s_warp, &block_total);
-    if (tid == 0) {
+    if (tid < 32) {
+        // decoupled look-back, one warp wide: lane l inspects predecessor bid-1-l, so a chain of aggregates
+        // resolves in one L2 round trip per 32 blocks instead of one per block
+        const uint32_t F = 0xffffffffu;
+        const uint64_t VAL = (1ull << 62) - 1;
+        const int lane = tid;
         uint64_t excl = 0;
         if (bid == 0) {
-            st_volatile_u64(&status[0], (2ull << 62) | (uint64_t)block_total);
+            if (lane == 0) st_volatile_u64(&status[0], (2ull << 62) | (uint64_t)block_total);
         } else {
-            st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
-            const uint64_t* p = &status[bid - 1];
+            if (lane == 0) st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
+            int p = (int)bid - 1;
             while (true) {
-                uint64_t s = ld_volatile_u64(p);
-                uint32_t f = (uint32_t)(s >> 62);
-                if (f == 0) continue;
-                excl += s & ((1ull << 62) - 1);
-                if (f == 2) break;
-                --p;
+                const int idx = p - lane;
+                const uint64_t s = idx >= 0 ? ld_volatile_u64(&status[idx]) : (2ull << 62);   // "block -1": inclusive 0
+                const uint32_t f = (uint32_t)(s >> 62);
+                const unsigned notready = __ballot_sync(F, f == 0);
+                const unsigned incl = __ballot_sync(F, f == 2);
+                const int first = incl ? __ffs(incl) - 1 : 32;
+                const unsigned need = first < 32 ? ((2u << first) - 1u) : F;   // lanes 0..first
+                if (notready & need) continue;                                  // not all published yet: look again
+                uint64_t part = (lane <= first) ? (s & VAL) : 0ull;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(F, part, o);
+                excl += part;
+                if (first < 32) break;
+                p -= 32;
             }
-            st_volatile_u64(&status[bid], (2ull << 62) | (excl + block_total));
+            if (lane == 0) st_volatile_u64(&status[bid], (2ull << 62) | (excl + block_total));
         }
-        s_prefix = excl;
-        if (bid == nblk - 1) *reinterpret_cast<uint64_t*>(misc + 2) = excl + block_total;
+        if (lane == 0) {
+            s_prefix = excl;
+            if (bid == nblk - 1) {
+                *reinterpret_cast<uint64_t*>(misc + 2) = excl + block_total;
+                if (host_total) {       // the host learns the count without a copy or a stream synchronisation
+                    host_total[0] = excl + block_total;
+                    __threadfence_system();
+                    host_total[1] = seq;
+                }
+            }
+        }
     }
     __syncthreads();
     uint32_t run = (uint32_t)s_prefix + texcl;

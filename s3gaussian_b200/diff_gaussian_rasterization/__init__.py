@@ -89,6 +89,21 @@ def release_cached_arenas():
     _POOL.clear()
 
 
+# Optional gradient sink.  By default the backward allocates its gradient tensors (rasterize_points.cu:154-163 does
+# the same); a data-parallel caller can instead route them into a communication buffer - e.g. a symmetric-memory
+# bucket that our peer all-reduce kernels sum in place (dp.PeerAllReduce) - so no gather copy sits between the
+# backward kernel and the collective.  The sink is any callable (name, shape, device) -> float32 tensor or None;
+# names: means3D, means2D, colors_precomp, opacities, cov3D_precomp, shs, scales, rotations.
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink):
+    """Install (or with None remove) the gradient sink; returns the previous one."""
+    global _GRAD_SINK
+    prev, _GRAD_SINK = _GRAD_SINK, sink
+    return prev
+
+
 def _ptr(t: torch.Tensor | None):
     """device pointer, or NULL for the reference's 'absent' empty tensors
     (torch.Tensor([]), DGR/.../__init__.py:198-208)."""
@@ -204,14 +219,20 @@ class _RasterizeGaussians(torch.autograd.Function):
         proj = _f32c(rs.projmatrix, dev)
         campos = _f32c(rs.campos, dev)
 
-        def e(*shape):
+        def e(name, *shape):
+            if _GRAD_SINK is not None:
+                t = _GRAD_SINK(name, shape, dev)
+                if t is not None:
+                    if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != dev:
+                        raise RuntimeError(f"gradient sink returned an unusable tensor for {name}")
+                    return t
             return torch.empty(shape, dtype=torch.float32, device=dev)
 
         # every element is written by the kernel (zeros where radii <= 0): no memsets
-        grad_means3D, grad_means2D = e(P, 3), e(P, 3)
-        grad_colors, grad_opacities = e(P, 3), e(P, 1)
-        grad_cov3D, grad_sh = e(P, 6), e(P, M, 3)
-        grad_scales, grad_rotations = e(P, 3), e(P, 4)
+        grad_means3D, grad_means2D = e("means3D", P, 3), e("means2D", P, 3)
+        grad_colors, grad_opacities = e("colors_precomp", P, 3), e("opacities", P, 1)
+        grad_cov3D, grad_sh = e("cov3D_precomp", P, 6), e("shs", P, M, 3)
+        grad_scales, grad_rotations = e("scales", P, 3), e("rotations", P, 4)
 
         args = (P, int(rs.sh_degree), M, ctx.num_rendered, _ptr(bg), W, H, _ptr(means3D), _ptr(sh),
                 _ptr(colors_precomp), _ptr(scales), float(rs.scale_modifier), _ptr(rotations),

@@ -358,3 +358,25 @@ def test_radix_sort_standalone(built_lib):
         _, perm = torch.sort(dig, stable=True)
         assert torch.equal(vo.to(torch.int64), perm), (n, b0, b1)
         assert torch.equal(ko, keys[perm])
+
+
+def test_binning_capacity_overflow_is_repeated_not_truncated(ours, oracle_lib):
+    """The forward enqueues the binning against the capacity remembered from the previous call on this thread and
+    checks the true instance count afterwards; a call whose count outgrew it must come out identical to a fresh
+    one (the tail is repeated with a larger arena), and a much smaller call after a big one must not see stale
+    state."""
+    from s3gaussian_b200 import synthetic as syn
+    small_cloud, small_cam = syn.make_small_scene(P=50, width=64, height=48, seed=31)
+    big_cloud, big_cam = syn.make_small_scene(P=6000, width=320, height=208, seed=32)
+    ds = util.scene_inputs(small_cloud, small_cam, mode="rgb")
+    db = util.scene_inputs(big_cloud, big_cam, mode="sh", sh_degree=2)
+    ob, os_ = util.oracle_run(oracle_lib, db), util.oracle_run(oracle_lib, ds)
+    assert ob["R"] > 20 * max(os_["R"], 1)
+    for d, o in ((ds, os_), (db, ob), (ds, os_), (db, ob)):
+        color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+        check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
+                                             tiles_touched=o["geometry"]["tiles_touched"],
+                                             point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                                             ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+        assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
+        assert util.relerr(depth.cpu().numpy(), o["depth"]) < TOL

@@ -411,7 +411,7 @@ def test_capture_restore_round_trip_with_reference_tuple(built_lib, tmp_path):
                 exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
 
     class Ref:
-        get_xyz = property(ns["get_xyz"])
+        get_xyz = ns["get_xyz"]        # the extracted FunctionDef keeps its @property decorator
         capture, restore, training_setup = ns["capture"], ns["restore"], ns["training_setup"]
     ref_dn, _ = ref_ext.load_ref_deform()
     res, mres = (16, 12, 10, 7), (1, 2)

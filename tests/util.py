@@ -103,9 +103,18 @@ def ours_forward_state(d, dev):
         xyAB=view(0, "xyAB", np.float32).reshape(-1, 4), Cod=view(0, "Cod", np.float32).reshape(-1, 4),
         rgb=view(0, "rgb", np.float32).reshape(-1, 4), tiles_touched=view(0, "tiles_touched", np.uint32),
         point_list=view(1, "point_list", np.uint32) if R > 0 else np.zeros(0, np.uint32),
-        point_list_tiles=view(1, "point_list_tiles", np.uint32) if R > 0 else np.zeros(0, np.uint32),
         ranges=view(2, "ranges", np.uint32).reshape(-1, 2), n_contrib=view(2, "n_contrib", np.uint32),
         final_T=view(2, "final_T", np.float32))
+    # The sorted tile ids (high 32 bits of the reference's sorted keys) are not materialised any more: the per-tile
+    # ranges come from the tile histogram.  Rebuild them from the ranges: tile t owns [start, end) of the list; the
+    # tests compare this against the reference's keys, which also checks that the ranges tile the list exactly.
+    rng = views["ranges"].astype(np.int64)
+    lens = rng[:, 1] - rng[:, 0]
+    tiles = np.full(R, 0xFFFFFFFF, np.uint32)
+    nz = np.nonzero(lens > 0)[0]
+    if nz.size and int(lens.sum()) == R and np.array_equal(rng[nz, 0], np.cumsum(lens[nz]) - lens[nz]):
+        tiles = np.repeat(nz.astype(np.uint32), lens[nz])
+    views["point_list_tiles"] = tiles
     return color, radii, depth, R, views
 
 

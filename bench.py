@@ -203,14 +203,39 @@ def main():
         if int(agree[0]) == 0:
             peer = None
 
+    # Gradient sink (ours, N > 1): the backward kernel writes the five per-Gaussian gradient tensors straight into
+    # the communication bucket (symmetric memory for the peer kernels, a plain flat tensor for NCCL) - no gather copy
+    # between the backward and the collective.  The reference arm keeps torch.cat + ncclAllReduce.
+    bucket, comm_ev = None, None
+    if world > 1 and a.impl == "ours":
+        names = {"means3D": t["means3D"], "shs": t["shs"], "colors_precomp": t["colors_precomp"],
+                 "opacities": t["opacities"], "scales": t["scales"], "rotations": t["rotations"]}
+        offs, n_tot = {}, 0
+        for k, v in names.items():
+            if v is not None:
+                offs[k] = (n_tot, v.numel())
+                n_tot += v.numel()
+        bucket = peer.flat(n_tot) if peer is not None else torch.zeros(n_tot, device=dev)
+
+        def sink(name, shape, device):
+            if name not in offs:
+                return None
+            o, n = offs[name]
+            return bucket[o:o + n].view(shape)
+        mod.set_grad_sink(sink)
+        comm_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
     def allreduce_grads():
         if world > 1:
-            grads = [v.grad.reshape(-1) for v in leaves if v is not m2d]
-            if peer is not None:
-                n = sum(g_.numel() for g_ in grads)
-                torch.cat(grads, out=peer.flat(n))
-                return peer.all_reduce_()
-            flat = torch.cat(grads)
+            if bucket is not None:
+                comm_ev[0].record()
+                if peer is not None:
+                    peer.all_reduce_()
+                else:
+                    dist.all_reduce(bucket)
+                comm_ev[1].record()
+                return bucket
+            flat = torch.cat([v.grad.reshape(-1) for v in leaves if v is not m2d])
             dist.all_reduce(flat)
             return flat
         return None
@@ -273,12 +298,14 @@ def main():
         e1.record()
         torch.cuda.synchronize()          # the reference launches on the legacy stream: device-wide sync
         ms = e0.elapsed_time(e1)
+        local_ms["last"] = ms
         if world > 1:
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.barrier()
             ms = float(tt[0])
         return ms
+    local_ms = {}
 
     if a.impl == "ours":
         from s3gaussian_b200 import _lib
@@ -287,6 +314,7 @@ def main():
     if sampler:
         sampler.start()
     ms_res = timed(step_resident, a.steps, max(a.warmup, 3))
+    ms_res_local = local_ms["last"]
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, a.steps, 3)
 
@@ -351,6 +379,25 @@ def main():
         step_ms = ms_res / a.steps
         roofline["step"] = {"algorithmic_bytes": int(step_bytes), "achieved": round(step_bytes / (step_ms * 1e-3) / 1e9, 2),
                             "frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / hbm, 4)}
+
+    # ---- per-rank breakdown (N > 1): every rank renders a different camera; the step is the max over ranks ----
+    per_rank = None
+    if world > 1:
+        comm_ms = None
+        if comm_ev is not None:
+            step_resident()
+            torch.cuda.synchronize()
+            comm_ms = round(comm_ev[0].elapsed_time(comm_ev[1]), 4)
+        mine = {"rank": rank, "step_ms": round(ms_res_local / a.steps, 4), "comm_ms": comm_ms, "visible": V,
+                "num_rendered": R,
+                "render_ms": (round(sum(stages["forward_ms"].values()) + sum(stages["backward_ms"].values()), 4)
+                              if stages else None)}
+        if bucket is not None:
+            o, n = offs["means3D"]
+            mine["sink_aliased"] = bool(t["means3D"].grad is not None and t["means3D"].grad.data_ptr() == bucket[o:o + n].data_ptr())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
 
     # ---- CPU baseline (rank 0, N == 1) -------------------------------------
     cpu = None
@@ -479,6 +526,13 @@ def main():
         out["train_iteration"] = train_it
     if configs:
         out["configs"] = configs
+    if per_rank:
+        out["per_rank"] = per_rank
+        nbytes = 4 * (bucket.numel() if bucket is not None else sum(v.numel() for v in leaves if v is not m2d))
+        cm = [r["comm_ms"] for r in per_rank if r.get("comm_ms")]
+        if nbytes and cm:
+            out["comm"] = {"bytes": int(nbytes), "ms_max": max(cm),
+                           "bus_gbs": round(2 * (world - 1) / world * nbytes / (max(cm) * 1e-3) / 1e9, 1)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -29,16 +29,18 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 
 def _timed(fn, steps, warmup):
+    """median milliseconds per call over `steps` calls, one CUDA event pair per call (a single allocator or
+    host hiccup inside a short loop would otherwise dominate the mean)"""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
         fn()
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    return float(np.median([evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]))
 
 
 # ------------------------------------------------------------------------------------------------ config 1
@@ -101,7 +103,7 @@ def config2(impl, mod, dev):
                 return rast(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], shs=t["shs"],
                             colors_precomp=t["colors_precomp"], scales=t["scales"], rotations=t["rotations"],
                             cov3D_precomp=None)
-        ms = _timed(fwd, 30, 5)
+        ms = _timed(fwd, 40, 10)
         radii = fwd()[1]
         out["sh_in_kernel" if mode == "sh" else "precomputed_colours"] = {
             "ms": round(ms, 4), "gaussians_per_s": round(P / (ms * 1e-3), 1), "visible": int((radii > 0).sum())}
@@ -153,9 +155,20 @@ def config3(impl, dev, hbm_gbs):
             do_render()
     ms = _timed(step, 8, 3)
     ms_f = _timed(fwd_only, 8, 2)
+    sorted_ms = None
+    if impl == "ours":
+        # the same step with the Gaussians in Morton order of their positions (GaussianModel.spatial_sort(), a
+        # framework feature: consecutive warps of the HexPlane kernels then share texels in L1)
+        del pc, leaves
+        pc = GaussianModelLite(cloud.morton_sorted(), net).to(dev)
+        leaves = list(pc.parameters())
+        sorted_ms = (_timed(step, 8, 3), _timed(fwd_only, 8, 2))
     out = {"what": f"{P} Gaussians, fine stage (HexPlane 4 levels x 6 planes x 32 ch + dx/dshs/feat heads), {W}x{H}, rgb + feat "
                    "passes, L1 + depth + feat + dx + dshs loss, backward",
            "ms_fwd_bwd": round(ms, 3), "ms_fwd": round(ms_f, 3), "gaussians_per_s": round(P / (ms * 1e-3), 1)}
+    if sorted_ms:
+        out["ms_fwd_bwd_spatially_sorted"] = round(sorted_ms[0], 3)
+        out["ms_fwd_spatially_sorted"] = round(sorted_ms[1], 3)
     if impl == "ours":
         # B_hex of SURVEY 8d: plane reads + plane-gradient scatter, min(P*12288, 142.9 MB) each, + P*216 B written
         b_hex = 2 * min(P * 12288, 142_909_440) + P * 216
@@ -261,7 +274,11 @@ def config4(impl, mod, dev, iterations=200):
             pc.optimizer.zero_grad(set_to_none=True)
         npoints = lambda: int(pc._xyz.shape[0])
 
-    # warm-up: a few plain iterations and one densify + prune event (allocator growth, first-touch)
+    # steady-state allocator for BOTH arms: the densify events grow every per-Gaussian tensor; a training run
+    # that has been going for a while serves those requests from torch's cache, a fresh process pays cudaMalloc
+    # (~100 ms per event).  Reserve once, outside the timed loop.
+    warm = [torch.empty(1 << 30, dtype=torch.uint8, device=dev) for _ in range(12)]
+    del warm
     torch.manual_seed(0)
     for w in range(1, 4):
         iteration(w, cams[w % len(cams)])

@@ -72,8 +72,12 @@ int s3g_mark_visible(int P, const float* means3D, const float* viewmatrix,
  * caller-allocated; the three opaque state buffers are grown through the
  * callbacks and are the forward->backward contract (their LAYOUT is ours, not
  * the reference's; use s3g_state_field() to look inside).
- * One blocking 4-byte D2H read happens inside (as rasterizer_impl.cu:282) to
- * size the binning arena. */
+ * num_rendered never stalls the GPU: the count stays on the device for the binning kernels and is ALSO stored by
+ * the scan kernel into mapped pinned host memory; the host reads it there after the whole forward has been enqueued
+ * against the binning capacity this thread requested last time (binning_alloc is called with that size first).  If
+ * the count outgrew the capacity - writes were clamped - the arena is grown through binning_alloc and the tail
+ * (emit, tile sort, composite) is enqueued again.  The very first call on a (thread, device) waits for the count
+ * before sizing the arena, like rasterizer_impl.cu:282.  No cudaMemcpy, event or stream synchronisation inside. */
 int64_t s3g_rasterize_forward(
     s3g_alloc_fn geom_alloc, void* geom_user,
     s3g_alloc_fn binning_alloc, void* binning_user,
@@ -146,7 +150,8 @@ int s3g_rasterize_backward(
  * layout for the given problem size and returns its byte offset from the
  * (128-byte aligned) buffer base, its element size and element count.
  * Fields: geometry: "xyAB","Cod","rgb","depth_key","tiles_touched","rect","clamped"
- *         binning : "point_list","point_list_tiles"
+ *         binning : "point_list" (first field: its offset does not depend on the arena capacity; the sorted tile
+ *                   ids are not materialised - "ranges" delimits every tile's slice of the list)
  *         image   : "final_T","n_contrib","ranges"
  * Returns S3G_OK or S3G_ERR_ARG. */
 int s3g_state_field(int buffer, const char* name, int64_t P, int64_t R, int width, int height,
@@ -158,7 +163,8 @@ size_t s3g_binning_bytes(int64_t R);
 size_t s3g_image_bytes(int width, int height);
 
 /* ---- HexPlane + deformation decoder + render() front-end -------------------
- * Replaces, fused into one forward and one backward kernel (csrc/deform.cuh):
+ * Replaces (forward: hexplane_sample_kernel -> tcgen05 decoder kernel; backward: mma.sync decoder kernel ->
+ * hexplane_scatter_kernel; csrc/deform.cuh, csrc/deform_tc.cuh):
  *   deform_network.forward_dynamic / Deformation.forward_dynamic   scene/deformation.py:108-166,216-231
  *   HexPlaneField.get_density / interpolate_ms_features             scene/hexplane.py:73-106,160-175
  *   scaling/rotation/opacity activations + convert_SHs_python      gaussian_renderer/__init__.py:99-117,

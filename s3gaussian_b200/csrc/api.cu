@@ -294,11 +294,10 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     pa.radii = radii; pa.xyAB = geom.xyAB; pa.Cod = geom.Cod; pa.rgb = geom.rgb;
     pa.depth_key = geom.depth_key; pa.tiles_touched = geom.tiles_touched; pa.rect = geom.rect;
     pa.clamped = geom.clamped; pa.order = geom.order_a;
-    pa.depth_hist = geom.sort.hist;
     pa.grid_x = tg.x; pa.grid_y = tg.y;
     g_timer.begin(0);
     // one memset for everything the chained scan and the depth sort expect zeroed (look-back words, tickets,
-    // digit histograms - the histograms are filled by the preprocess kernel)
+    // digit histograms)
     S3G_CUDA(cudaMemsetAsync(geom.scan_status, 0, geom.zero_bytes, stream), "memset scan/sort state");
     S3G_MARK(0, "preprocess_forward");
     {
@@ -321,7 +320,8 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
 
     // ---- depth digits of the LSD sort, over Gaussians --------------------
     S3G_CUDA(radix_sort_pairs((uint32_t)P, geom.depth_key, geom.order_a, geom.key_b, geom.order_b,
-                              nullptr, geom.order_a, 0, 32, geom.sort, stream, nullptr, /*hist_ready=*/true),
+                              nullptr, geom.order_a, 0, 32, geom.sort, stream, nullptr, /*hist_ready=*/false,
+                              /*prepared=*/true),
              "depth sort");
     S3G_STAGE("depth sort");
 
@@ -372,8 +372,9 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
                     S3G_CUDA(cudaFuncSetAttribute(emit_instances_kernel<true>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem),
                              "emit smem attribute");
-                const int grid = std::min(blocks_needed, 148 * 4);
-                emit_instances_kernel<true><<<grid, 256, hist_smem, stream>>>(
+                // two 512-thread blocks per SM: the private histogram is zeroed and flushed once per block
+                const int grid = std::min((P + 511) / 512, 148 * 2);
+                emit_instances_kernel<true><<<grid, 512, hist_smem, stream>>>(
                     (uint32_t)P, geom.order_a, geom.offsets, geom.tiles_touched, geom.rect, tg.x, n_tiles,
                     (uint32_t)cap, bin.tile_a, bin.idx_a, img.tile_hist);
             } else {
@@ -387,7 +388,7 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
         {
             const int npass = (tile_bits + RADIX_BITS - 1) / RADIX_BITS;
             tile_offsets_kernel<<<1, 1024, 0, stream>>>(n_tiles, img.tile_hist, img.ranges, npass, tile_bits,
-                                                        bin.sort.hist);
+                                                        bin.sort.hist, n_dev, (uint32_t)cap);
         }
         S3G_STAGE("tile offsets");
         S3G_MARK(0, "tile_sort");

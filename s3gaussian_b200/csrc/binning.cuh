@@ -29,7 +29,7 @@ namespace s3g {
 // `cap` bounds the writes: the binning arena is sized before the instance count is known on the
 // host (see s3g_rasterize_forward); an overflowing call is detected there and repeated.
 template <bool SMEM_HIST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 emit_instances_kernel(uint32_t P, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ tiles_touched, const ushort4* __restrict__ rect,
@@ -101,49 +101,45 @@ emit_instances_kernel(uint32_t P, const uint32_t* __restrict__ order,
 
 // Exclusive scan of the tile histogram -> per-tile ranges (rasterizer_impl.cu:116-138: [start,end) of
 // every touched tile, zeros elsewhere, :311) and the digit histograms of the npass 8-bit passes
-// of the tile-id sort.  One block; tiles are walked in chunks of blockDim.x.
+// of the tile-id sort.  One block; every thread owns a run of consecutive tiles.
+// If the instance count outgrew the capacity the lists are incomplete: every range is written empty, so the
+// composite of this attempt draws the background only (the host repeats the tail with a larger arena).
 __global__ void __launch_bounds__(1024)
 tile_offsets_kernel(uint32_t n_tiles, const uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges,
-                    int npass, int end_bit, uint32_t* __restrict__ digit_hist /*[npass][RADIX]*/) {
+                    int npass, int end_bit, uint32_t* __restrict__ digit_hist /*[npass][RADIX]*/,
+                    const uint32_t* __restrict__ n_dev, uint32_t cap) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_dig[SORT_MAX_PASSES][RADIX];
-    __shared__ uint32_t s_run;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < SORT_MAX_PASSES * RADIX; i += blockDim.x) (&s_dig[0][0])[i] = 0;
-    if (tid == 0) s_run = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
-        const uint32_t t = base + tid;
-        const uint32_t c = t < n_tiles ? tile_hist[t] : 0u;
-        uint32_t inc = c;
+    const bool overflow = n_dev != nullptr && *n_dev > cap;
+    const uint32_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t t0 = min(n_tiles, (uint32_t)tid * per), t1 = min(n_tiles, t0 + per);
+    uint32_t sum = 0;
+    for (uint32_t t = t0; t < t1; ++t) sum += tile_hist[t];
+    uint32_t inc = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, tot = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            const uint32_t v = s_warp[w];
-            if (w < warp) wbase += v;
-            tot += v;
-        }
-        const uint32_t start = s_run + wbase + inc - c;
-        if (t < n_tiles) {
-            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            if (c) {
-                for (int p = 0; p < npass; ++p) {
-                    const int shift = p * RADIX_BITS;
-                    const int bits = min(RADIX_BITS, end_bit - shift);
-                    atomicAdd(&s_dig[p][(t >> shift) & ((1u << bits) - 1u)], c);
-                }
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();      // also orders the s_dig zeroing before the atomics below
+    uint32_t run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t c = tile_hist[t];
+        ranges[t] = (c && !overflow) ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+        if (c) {
+            for (int p = 0; p < npass; ++p) {
+                const int shift = p * RADIX_BITS;
+                const int bits = min(RADIX_BITS, end_bit - shift);
+                atomicAdd(&s_dig[p][(t >> shift) & ((1u << bits) - 1u)], c);
             }
         }
-        __syncthreads();
-        if (tid == 0) s_run += tot;
-        __syncthreads();
+        run += c;
     }
+    __syncthreads();
     for (int i = tid; i < npass * RADIX; i += blockDim.x) digit_hist[i] = (&s_dig[0][0])[i];
 }
 

@@ -159,11 +159,13 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
                     const bool ok = alive && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     const bool stop = ok && (test_T < 0.0001f);
                     const bool blend = ok && !stop;
-                    const float ae = blend ? alpha : 0.0f;
-                    C0 += col.x * ae * T;
-                    C1 += col.y * ae * T;
-                    C2 += col.z * ae * T;
-                    D += col.w * ae * T;
+                    // weight alpha * T once (the reference multiplies feature * alpha * T per channel,
+                    // forward.cu:358-360: same value up to one rounding)
+                    const float wgt = blend ? alpha * T : 0.0f;
+                    C0 = fmaf(col.x, wgt, C0);
+                    C1 = fmaf(col.y, wgt, C1);
+                    C2 = fmaf(col.z, wgt, C2);
+                    D = fmaf(col.w, wgt, D);
                     T = blend ? test_T : T;
                     last_contributor = blend ? idx_base + (uint32_t)bit : last_contributor;
                     alive = alive && !stop;

@@ -200,7 +200,6 @@ struct PreFwdArgs {
     ushort4* rect;
     uint8_t* clamped;
     uint32_t* order;   // identity permutation, input of the depth sort
-    uint32_t* depth_hist;   // [4][256] digit histograms of depth_key for the LSD sort (pre-zeroed)
     int grid_x, grid_y;
 };
 
@@ -366,18 +365,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(PreFwdA
         }
     } else if (vis) {
         col = {a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]};
-    }
-    // digit histograms of the depth keys (all four 8-bit passes of the LSD sort that follows), one atomic per
-    // distinct digit per warp: saves the sort its own read of the keys
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-        const uint32_t key = vis ? __float_as_uint(po.depth) : DEPTH_KEY_INVISIBLE;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const uint32_t dgt = (key >> (8 * p)) & 255u;
-            const unsigned peers = __match_any_sync(vm, dgt);
-            if (lane == __ffs(peers) - 1) atomicAdd(&a.depth_hist[p * 256 + dgt], (uint32_t)__popc(peers));
-        }
     }
     if (!vis) return;
     const float opacity = a.opacities[idx];

@@ -70,13 +70,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 // The sort kernels and their host driver are compiled in their own translation unit (radix_sort.cu,
 // which defines S3G_RADIX_SORT_IMPL); everyone else sees the declaration only.
 // n: item count known on the host, or the capacity when `n_dev` (device word with the true count, clamped to n)
-// is given.  hist_ready: the caller zeroed the temp block (radix_sort_prepare) and a producer kernel already
-// wrote the digit histograms st.hist[pass][digit]; otherwise the driver zeroes and runs sort_histogram_kernel.
+// is given.  prepared: the caller already zeroed the temp block (radix_sort_prepare, e.g. folded into a larger
+// memset).  hist_ready (implies prepared): a producer kernel already wrote the digit histograms
+// st.hist[pass][digit]; otherwise the driver runs sort_histogram_kernel.
 cudaError_t radix_sort_prepare(const SortTemp& st, cudaStream_t stream);
 cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_tmp,
                              uint32_t* vals_tmp, uint32_t* keys_final, uint32_t* vals_final, int begin_bit,
                              int end_bit, const SortTemp& st, cudaStream_t stream,
-                             const uint32_t* n_dev = nullptr, bool hist_ready = false);
+                             const uint32_t* n_dev = nullptr, bool hist_ready = false, bool prepared = false);
 
 #ifdef S3G_RADIX_SORT_IMPL
 // ---- histogram of every digit of every pass in one read of the keys -------
@@ -112,7 +113,7 @@ sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int begin_b
 // ---- one digit pass --------------------------------------------------------
 // grid: exactly ceil(n / SORT_TILE) blocks.  status: [nblk][RADIX] zeroed.
 template <bool WRITE_KEYS>
-__global__ void __launch_bounds__(SORT_THREADS, 4)   // 64 registers: four 43 KB blocks per SM (ranking is a latency chain)
+__global__ void __launch_bounds__(SORT_THREADS)   // (capping at 64 registers for a 4th block per SM measured slower)
 sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                      const uint32_t* __restrict__ n_dev, int shift, uint32_t mask,
@@ -162,6 +163,14 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         rank[i] = old + __popc(peers & lt);
         __syncwarp();
     }
+    // the values are only needed for the scatter; fetching them here (not there) keeps the global round
+    // trip off the critical path behind the look-back
+    uint32_t v_in[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        uint32_t idx = base + i * 32 + lane;
+        v_in[i] = idx < n ? vals_in[idx] : 0u;
+    }
     __syncthreads();
     // digit tid: exclusive prefix over warps, block count
     uint32_t count = 0;
@@ -210,14 +219,6 @@ sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     s_gofs[tid] = hexcl + excl - dstart;
     __syncthreads();
 
-    // the values are only needed from here on (16 more live registers across the look-back cost a fourth
-    // resident block per SM)
-    uint32_t v_in[SORT_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t idx = base + i * 32 + lane;
-        v_in[i] = idx < n ? vals_in[idx] : 0u;
-    }
     // scatter to the block-local digit-sorted order in shared memory
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -253,7 +254,7 @@ cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
                                     uint32_t* keys_tmp, uint32_t* vals_tmp, uint32_t* keys_final,
                                     uint32_t* vals_final, int begin_bit, int end_bit,
                                     const SortTemp& st, cudaStream_t stream, const uint32_t* n_dev,
-                                    bool hist_ready) {
+                                    bool hist_ready, bool prepared) {
     if (n == 0) return cudaSuccess;
     int bits = end_bit - begin_bit;
     int npass = (bits + RADIX_BITS - 1) / RADIX_BITS;
@@ -261,8 +262,10 @@ cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
     if (npass > SORT_MAX_PASSES) return cudaErrorInvalidValue;
     const uint32_t nblk = (uint32_t)div_up64(n, SORT_TILE);
     if (!hist_ready) {
-        cudaError_t e = radix_sort_prepare(st, stream);
-        if (e != cudaSuccess) return e;
+        if (!prepared) {
+            cudaError_t e = radix_sort_prepare(st, stream);
+            if (e != cudaSuccess) return e;
+        }
         if (n_dev) return cudaErrorInvalidValue;       // a device-side count needs a producer-built histogram
         uint32_t hgrid = nblk < 148u * 8u ? nblk : 148u * 8u;
         sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, stream>>>(keys_in, n, begin_bit, end_bit, npass,

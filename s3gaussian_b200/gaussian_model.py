@@ -354,6 +354,39 @@ class GaussianModel:
             self.denom = torch.zeros((n_out, 1), device=dev)
             self.max_radii2D = torch.zeros(n_out, device=dev)
 
+    def spatial_sort(self):
+        """Reorder every per-Gaussian tensor (parameters, Adam moments, densification accumulators) along a Morton
+        curve of the positions (10 bits per axis over the bounding box).  Not in the reference - its Gaussians stay
+        in LiDAR / append order - and a no-op for the maths: every kernel is order-independent up to the order of
+        fp32 additions.  What it buys: consecutive warps of the HexPlane sample / scatter kernels (one warp per
+        Gaussian) then touch neighbouring texels, so L1 absorbs most of the 12 KB-per-Gaussian plane traffic that
+        otherwise goes to L2.  Cheap (one radix sort + one row gather); call it after densify / prune.  Returns the
+        permutation (new row i = old row order[i])."""
+        lib = _lib.load()
+        with torch.no_grad():
+            xyz = self._xyz.data
+            P = xyz.shape[0]
+            if P < 2:
+                return torch.arange(P, device=xyz.device)
+            lo, hi = xyz.min(0).values, xyz.max(0).values
+            q = ((xyz - lo) / (hi - lo).clamp_min(1e-12) * 1023.999).to(torch.int64).clamp_(0, 1023)
+
+            def spread(v):      # 10 bits -> every third bit
+                v = (v | (v << 16)) & 0x030000FF
+                v = (v | (v << 8)) & 0x0300F00F
+                v = (v | (v << 4)) & 0x030C30C3
+                return (v | (v << 2)) & 0x09249249
+            key = (spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)).to(torch.int32).contiguous()
+            idx = torch.arange(P, device=xyz.device, dtype=torch.int32)
+            ko, vo = torch.empty_like(key), torch.empty_like(idx)
+            tmp = torch.empty(lib.s3g_sort_temp_bytes(P), dtype=torch.uint8, device=xyz.device)
+            _lib.check(lib.s3g_sort_pairs_u32(P, key.data_ptr(), idx.data_ptr(), ko.data_ptr(), vo.data_ptr(), 0, 30,
+                                              tmp.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "s3g_sort_pairs_u32")
+            order = vo.to(torch.int64)
+            self._rebuild(order, P, keep_accumulators=True)
+        return order
+
     def prune_points(self, mask):
         """gaussian_model.py:441-455."""
         keep = torch.nonzero(~mask, as_tuple=False).squeeze(1)

@@ -113,6 +113,23 @@ class GaussianCloud:
         return GaussianCloud(*(t.to(device) for t in (self.xyz, self.features_dc, self.features_rest,
                                                       self.scaling, self.rotation, self.opacity)))
 
+    def morton_sorted(self):
+        """The same cloud with its rows permuted along a Morton curve of the positions (what
+        GaussianModel.spatial_sort() does to a live model; host-side torch, data preparation only)."""
+        xyz = self.xyz.detach().cpu()
+        lo, hi = xyz.min(0).values, xyz.max(0).values
+        q = ((xyz - lo) / (hi - lo).clamp_min(1e-12) * 1023.999).to(torch.int64).clamp_(0, 1023)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        key = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+        order = torch.argsort(key, stable=True).to(self.xyz.device)
+        return GaussianCloud(*(t[order] for t in (self.xyz, self.features_dc, self.features_rest, self.scaling,
+                                                  self.rotation, self.opacity)))
+
     # the reference's activations (scene/gaussian_model.py:39-47)
     def get_scaling(self):
         return torch.exp(self.scaling)

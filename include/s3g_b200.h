@@ -145,6 +145,77 @@ int s3g_rasterize_backward(
     int debug,
     void* stream);
 
+/* ---- one binning, two colour sets -------------------------------------------------
+ * render(render_feat=True) rasterizes the same Gaussians twice - once with the RGB colours, once with the
+ * three-channel feature colours (gaussian_renderer/__init__.py:173-186, train.py:373) - and the reference runs its
+ * whole rasterizer again for the second image.  The *_aux entry points composite both colour sets in ONE pass over
+ * one preprocess + one sort: `colors_aux` [P,3] -> `out_color_aux` [3,H,W] (same background), and in the backward
+ * `dL_dpix_aux` [3,H,W] -> `dL_dcolor_aux` [P,3]; every other argument and output means what it means in
+ * s3g_rasterize_forward / s3g_rasterize_backward, the geometry gradients are those of the SUM of both images'
+ * losses. */
+int64_t s3g_rasterize_forward_aux(
+    s3g_alloc_fn geom_alloc, void* geom_user,
+    s3g_alloc_fn binning_alloc, void* binning_user,
+    s3g_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    float* out_depth,
+    int* radii,
+    int debug,
+    void* stream,
+    const float* colors_aux,
+    float* out_color_aux);
+int s3g_rasterize_backward_aux(
+    int P, int D, int M, int64_t R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer,
+    char* binning_buffer,
+    char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_ddepth,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    int debug,
+    void* stream,
+    const float* dL_dpix_aux,
+    float* dL_dcolor_aux);
+
 /* ---- state-buffer introspection (tests / debugging) ---------------------
  * buffer: 0 = geometry, 1 = binning, 2 = image.  Looks up a named field of our
  * layout for the given problem size and returns its byte offset from the

@@ -31,6 +31,12 @@ SIGNATURES = {
     "s3g_rasterize_backward": (_I, [_I, _I, _I, _I64, _V, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V,
                                     _V, _F, _F, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
                                     _V, _V, _V, _I, _V]),
+    "s3g_rasterize_forward_aux": (_I64, [ALLOC_FN, _V, ALLOC_FN, _V, ALLOC_FN, _V, _I, _I, _I, _V, _I, _I,
+                                          _V, _V, _V, _V, _V, _F, _V, _V, _V, _V, _V, _F, _F, _I, _V, _V,
+                                          _V, _I, _V, _V, _V]),
+    "s3g_rasterize_backward_aux": (_I, [_I, _I, _I, _I64, _V, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V,
+                                        _V, _F, _F, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
+                                        _V, _V, _V, _I, _V, _V, _V]),
     "s3g_state_field": (_I, [_I, C.c_char_p, _I64, _I64, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ),
                              C.POINTER(_SZ)]),
     # struct pointers (s3g_deform_net / s3g_deform_net_grads) are passed with ctypes.byref()

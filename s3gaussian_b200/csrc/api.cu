@@ -238,7 +238,10 @@ int s3g_sort_pairs_u32(int64_t n, uint32_t* keys_in, uint32_t* vals_in, uint32_t
     return S3G_OK;
 }
 
-int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binning_alloc,
+}  // extern "C"
+
+namespace {
+int64_t forward_impl(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binning_alloc,
                               void* binning_user, s3g_alloc_fn image_alloc, void* image_user, int P,
                               int D, int M, const float* background, int width, int height,
                               const float* means3D, const float* shs, const float* colors_precomp,
@@ -246,14 +249,18 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
                               const float* rotations, const float* cov3D_precomp,
                               const float* viewmatrix, const float* projmatrix, const float* cam_pos,
                               float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
-                              float* out_depth, int* radii, int debug, void* stream_) {
+                              float* out_depth, int* radii, int debug, void* stream_,
+                              const float* colors_aux, float* out_aux) {
     (void)prefiltered;   // the reference only uses it for a device-side trap (auxiliary.h:156-160)
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || width <= 0 || height <= 0) return fail(S3G_ERR_ARG, "forward: bad sizes");
     if (!geom_alloc || !binning_alloc || !image_alloc) return fail(S3G_ERR_ARG, "forward: null allocator");
     if (!out_color || !out_depth || !background) return fail(S3G_ERR_ARG, "forward: null output/background");
     const size_t HW = (size_t)width * height;
+    if ((colors_aux != nullptr) != (out_aux != nullptr))
+        return fail(S3G_ERR_ARG, "forward: colors_aux and out_color_aux go together");
     if (P == 0) {   // rasterize_points.cu:82: outputs stay zero-filled
+        if (out_aux) S3G_CUDA(cudaMemsetAsync(out_aux, 0, 3 * HW * sizeof(float), stream), "memset aux");
         S3G_CUDA(cudaMemsetAsync(out_color, 0, 3 * HW * sizeof(float), stream), "memset color");
         S3G_CUDA(cudaMemsetAsync(out_depth, 0, HW * sizeof(float), stream), "memset depth");
         return 0;
@@ -292,6 +299,7 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     pa.focal_y = height / (2.0f * tan_fovy);   // rasterizer_impl.cu:223-224
     pa.focal_x = width / (2.0f * tan_fovx);
     pa.radii = radii; pa.xyAB = geom.xyAB; pa.Cod = geom.Cod; pa.rgb = geom.rgb;
+    pa.colors_aux = colors_aux; pa.aux = geom.aux;
     pa.depth_key = geom.depth_key; pa.tiles_touched = geom.tiles_touched; pa.rect = geom.rect;
     pa.clamped = geom.clamped; pa.order = geom.order_a;
     pa.grid_x = tg.x; pa.grid_y = tg.y;
@@ -403,7 +411,9 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
         ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb; ra.bg = background;
         ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
         ra.out_color = out_color; ra.out_depth = out_depth;
-        render_forward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+        ra.aux = geom.aux; ra.out_aux = out_aux;
+        if (colors_aux) render_forward_kernel<true><<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
+        else render_forward_kernel<false><<<dim3(tg.x, tg.y), TILE_PIX, 0, stream>>>(ra);
         S3G_STAGE("render_forward");
         S3G_MARK(0, nullptr);
 
@@ -423,7 +433,7 @@ int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_allo
     return R;
 }
 
-int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* background, int width,
+int backward_impl(int P, int D, int M, int64_t R, const float* background, int width,
                            int height, const float* means3D, const float* shs,
                            const float* colors_precomp, const float* scales, float scale_modifier,
                            const float* rotations, const float* cov3D_precomp,
@@ -433,7 +443,7 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
                            const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
                            float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
                            float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                           int debug, void* stream_) {
+                           int debug, void* stream_, const float* dL_dpix_aux, float* dL_dcolor_aux) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(S3G_ERR_ARG, "backward: bad sizes");
     if (P == 0) return S3G_OK;   // rasterize_points.cu:165
@@ -444,6 +454,9 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
         !dL_drot)
         return fail(S3G_ERR_ARG, "backward: null gradient output");
+    if ((dL_dpix_aux != nullptr) != (dL_dcolor_aux != nullptr))
+        return fail(S3G_ERR_ARG, "backward: dL_dpix_aux and dL_dcolor_aux go together");
+    const bool use_aux = dL_dpix_aux != nullptr;
     const bool use_sh = (colors_precomp == nullptr);
     if (use_sh && (!shs || !dL_dsh || !campos)) return fail(S3G_ERR_ARG, "backward: SH path needs shs, dL_dsh, campos");
     if (!cov3D_precomp && (!scales || !rotations))
@@ -466,17 +479,24 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
         ra.bg = background; ra.xyAB = geom.xyAB; ra.Cod = geom.Cod; ra.rgb = geom.rgb;
         ra.final_T = img.final_T; ra.n_contrib = img.n_contrib;
         ra.dL_dpix = dL_dpix; ra.dL_dpix_depth = dL_dpix_depth; ra.grad_rec = geom.grad_rec;
+        ra.aux = geom.aux; ra.dL_dpix_aux = dL_dpix_aux;
         // > 48 KB of dynamic shared memory needs the opt-in, once per device
         static unsigned long long attr_done = 0;
         int devid = 0;
         S3G_CUDA(cudaGetDevice(&devid), "cudaGetDevice");
         if (devid >= 64 || !((attr_done >> devid) & 1ull)) {
-            S3G_CUDA(cudaFuncSetAttribute(render_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(RenderBwdSmem)),
+            S3G_CUDA(cudaFuncSetAttribute(render_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(RenderBwdSmem<false>)),
+                     "render_backward smem attribute");
+            S3G_CUDA(cudaFuncSetAttribute(render_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(RenderBwdSmem<true>)),
                      "render_backward smem attribute");
             if (devid < 64) attr_done |= 1ull << devid;
         }
-        render_backward_kernel<<<dim3(tg.x, tg.y), TILE_PIX, sizeof(RenderBwdSmem), stream>>>(ra);
+        if (use_aux)
+            render_backward_kernel<true><<<dim3(tg.x, tg.y), TILE_PIX, sizeof(RenderBwdSmem<true>), stream>>>(ra);
+        else
+            render_backward_kernel<false><<<dim3(tg.x, tg.y), TILE_PIX, sizeof(RenderBwdSmem<false>), stream>>>(ra);
         S3G_STAGE("render_backward");
     }
 
@@ -495,7 +515,7 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy;
     pb.grad_rec = geom.grad_rec;
     pb.dL_dmean2D = dL_dmean2D; pb.dL_dconic = dL_dconic; pb.dL_dopacity = dL_dopacity;
-    pb.dL_dcolor = dL_dcolor; pb.dL_ddepth = dL_ddepth; pb.dL_dmean3D = dL_dmean3D;
+    pb.dL_dcolor = dL_dcolor; pb.dL_dcolor_aux = dL_dcolor_aux; pb.dL_ddepth = dL_ddepth; pb.dL_dmean3D = dL_dmean3D;
     pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = use_sh ? dL_dsh : nullptr;
     pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot;
     {
@@ -515,6 +535,78 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
     S3G_STAGE("preprocess_backward");
     S3G_MARK(1, nullptr);
     return S3G_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t s3g_rasterize_forward(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binning_alloc,
+                              void* binning_user, s3g_alloc_fn image_alloc, void* image_user, int P,
+                              int D, int M, const float* background, int width, int height,
+                              const float* means3D, const float* shs, const float* colors_precomp,
+                              const float* opacities, const float* scales, float scale_modifier,
+                              const float* rotations, const float* cov3D_precomp,
+                              const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                              float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                              float* out_depth, int* radii, int debug, void* stream) {
+    return forward_impl(geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, P, D, M, background,
+                        width, height, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+                        cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color,
+                        out_depth, radii, debug, stream, nullptr, nullptr);
+}
+
+int64_t s3g_rasterize_forward_aux(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binning_alloc,
+                                  void* binning_user, s3g_alloc_fn image_alloc, void* image_user, int P,
+                                  int D, int M, const float* background, int width, int height,
+                                  const float* means3D, const float* shs, const float* colors_precomp,
+                                  const float* opacities, const float* scales, float scale_modifier,
+                                  const float* rotations, const float* cov3D_precomp,
+                                  const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                                  float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                                  float* out_depth, int* radii, int debug, void* stream,
+                                  const float* colors_aux, float* out_color_aux) {
+    if (!colors_aux || !out_color_aux) return fail(S3G_ERR_ARG, "forward_aux: null aux colours / aux image");
+    return forward_impl(geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, P, D, M, background,
+                        width, height, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+                        cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color,
+                        out_depth, radii, debug, stream, colors_aux, out_color_aux);
+}
+
+int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* background, int width,
+                           int height, const float* means3D, const float* shs,
+                           const float* colors_precomp, const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* campos,
+                           float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                           char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                           const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
+                           float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                           float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                           int debug, void* stream) {
+    return backward_impl(P, D, M, R, background, width, height, means3D, shs, colors_precomp, scales, scale_modifier,
+                         rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                         binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity,
+                         dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream, nullptr,
+                         nullptr);
+}
+
+int s3g_rasterize_backward_aux(int P, int D, int M, int64_t R, const float* background, int width,
+                               int height, const float* means3D, const float* shs,
+                               const float* colors_precomp, const float* scales, float scale_modifier,
+                               const float* rotations, const float* cov3D_precomp,
+                               const float* viewmatrix, const float* projmatrix, const float* campos,
+                               float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                               char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                               const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
+                               float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                               float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                               int debug, void* stream, const float* dL_dpix_aux, float* dL_dcolor_aux) {
+    if (!dL_dpix_aux || !dL_dcolor_aux) return fail(S3G_ERR_ARG, "backward_aux: null aux gradients");
+    return backward_impl(P, D, M, R, background, width, height, means3D, shs, colors_precomp, scales, scale_modifier,
+                         rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                         binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity,
+                         dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream,
+                         dL_dpix_aux, dL_dcolor_aux);
 }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ struct GeomState {
     float4* xyAB;            // {pix.x, pix.y, conic.x, conic.y}          (forward.cu:252-254)
     float4* Cod;             // {conic.z, opacity, tau_cull, own index (bits)}
     float4* rgb;             // {r,g,b, view depth}: SH colour or copy of colors_precomp (forward.cu:243-246)
+    float4* aux;             // {r,g,b,-} of the optional second colour set composited on the same lists
     uint32_t* depth_key;     // float bits of depth, or DEPTH_KEY_INVISIBLE
     uint32_t* tiles_touched; // forward.cu:255
     ushort4* rect;           // {min.x, min.y, max.x, max.y} of getRect (auxiliary.h:46-56)
@@ -93,6 +94,7 @@ struct GeomState {
         g.xyAB = c.take<float4>(P);
         g.Cod = c.take<float4>(P);
         g.rgb = c.take<float4>(P);
+        g.aux = c.take<float4>(P);
         g.depth_key = c.take<uint32_t>(P);
         g.tiles_touched = c.take<uint32_t>(P);
         g.rect = c.take<ushort4>(P);
@@ -160,7 +162,7 @@ struct ImageState {
 // Raster-gradient record accumulated by the backward composite (one 64-byte
 // line per Gaussian so a warp's reduced partial sums land in two sectors).
 //   [0..1] dL/dmean2D.xy   [2..4] dL/dconic (x,y,w)   [5] dL/dopacity
-//   [6..8] dL/dcolour      [9]    dL/ddepth           [10..15] pad
+//   [6..8] dL/dcolour      [9]    dL/ddepth           [10..12] dL/d(aux colour)   [13..15] pad
 constexpr int GRAD_REC = 16;
 
 // host launch-parameter helpers

@@ -62,11 +62,13 @@ struct RenderFwdArgs {
     const float4* xyAB;
     const float4* Cod;
     const float4* rgb;
+    const float4* aux;       // second colour set composited on the same lists (AUX kernels), or NULL
     const float* bg;
     float* final_T;
     uint32_t* n_contrib;
     float* out_color;
     float* out_depth;
+    float* out_aux;          // [3,H,W] or NULL
 };
 
 // One staged instance: 48 bytes = three 16-byte gathers.  Lane j of the cull
@@ -78,8 +80,12 @@ struct __align__(16) Rec {
     float4 c;   // r, g, b, depth
 };
 
+// AUX: a second colour set (the feature image of render(render_feat=True), train.py:373) is composited in the
+// same walk - the reference runs its whole rasterizer a second time on identical geometry for it.
+template <bool AUX>
 __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs a) {
     __shared__ Rec s_rec[2][CB];
+    __shared__ float4 s_aux[AUX ? 2 : 1][AUX ? CB : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
     float T = 1.0f;
     uint32_t last_contributor = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    float A0 = 0.f, A1 = 0.f, A2 = 0.f;
     bool alive = inside;
 
     // prologue: gather batch 0, fetch the id of batch 1
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
         cp_async16(&s_rec[0][tid].a, &a.xyAB[id]);
         cp_async16(&s_rec[0][tid].b, &a.Cod[id]);
         cp_async16(&s_rec[0][tid].c, &a.rgb[id]);
+        if (AUX) cp_async16(&s_aux[0][tid], &a.aux[id]);
     }
     cp_async_commit();
     if (CB + tid < n) id_next = a.point_list[range.x + CB + tid];
@@ -122,6 +130,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
             cp_async16(&s_rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
             cp_async16(&s_rec[buf ^ 1][tid].b, &a.Cod[id_next]);
             cp_async16(&s_rec[buf ^ 1][tid].c, &a.rgb[id_next]);
+            if (AUX) cp_async16(&s_aux[buf ^ 1][tid], &a.aux[id_next]);
         }
         cp_async_commit();
         if ((b + 2) * CB + tid < n) id_next = a.point_list[range.x + (b + 2) * CB + tid];
@@ -166,6 +175,12 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
                     C1 = fmaf(col.y, wgt, C1);
                     C2 = fmaf(col.z, wgt, C2);
                     D = fmaf(col.w, wgt, D);
+                    if (AUX) {
+                        const float4 ax = s_aux[buf][c0 + bit];
+                        A0 = fmaf(ax.x, wgt, A0);
+                        A1 = fmaf(ax.y, wgt, A1);
+                        A2 = fmaf(ax.z, wgt, A2);
+                    }
                     T = blend ? test_T : T;
                     last_contributor = blend ? idx_base + (uint32_t)bit : last_contributor;
                     alive = alive && !stop;
@@ -188,6 +203,11 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_kernel(RenderFwdArgs 
         a.out_color[1 * HW + pix_id] = C1 + T * a.bg[1];
         a.out_color[2 * HW + pix_id] = C2 + T * a.bg[2];
         a.out_depth[pix_id] = D;
+        if (AUX) {
+            a.out_aux[0 * HW + pix_id] = A0 + T * a.bg[0];
+            a.out_aux[1 * HW + pix_id] = A1 + T * a.bg[1];
+            a.out_aux[2 * HW + pix_id] = A2 + T * a.bg[2];
+        }
     }
 }
 
@@ -203,6 +223,8 @@ struct RenderBwdArgs {
     const uint32_t* n_contrib;
     const float* dL_dpix;        // [3,H,W]
     const float* dL_dpix_depth;  // [1,H,W]
+    const float4* aux;           // second colour set (AUX kernels) or NULL
+    const float* dL_dpix_aux;    // [3,H,W] or NULL
     float* grad_rec;             // [P][GRAD_REC], zeroed
 };
 
@@ -241,8 +263,11 @@ constexpr int BCB = 128;          // instances per staged batch (backward)
 constexpr int BKS = 16;           // survivor slots per warp
 constexpr int BXW_STRIDE = 33;    // float2 row stride of the slot table: conflict-free for both phases
 
+template <bool AUX>
 struct RenderBwdSmem {
     Rec rec[2][BCB];                       // 12 KB
+    float4 aux[AUX ? 2 : 1][AUX ? BCB : 1];
+    float4 dpix_aux[AUX ? 8 : 1][AUX ? 32 : 1];   // dL/dpix of the second image
     float2 xw[8][BKS][BXW_STRIDE];         // 33 KB  {X, w} per (slot, pixel)
     float4 slot_a[8][BKS];                 // {pix.x, pix.y, conic.x, conic.y}
     float4 slot_b[8][BKS];                 // {conic.z, opacity, -, id bits}
@@ -250,13 +275,15 @@ struct RenderBwdSmem {
     uint32_t max_contrib;
 };
 
-__device__ __forceinline__ void bwd_flush(const RenderBwdSmem& sm, int warp, int lane, int ns, float cx, float cy,
+template <bool AUX>
+__device__ __forceinline__ void bwd_flush(const RenderBwdSmem<AUX>& sm, int warp, int lane, int ns, float cx, float cy,
                                           float ddelx_dx, float ddely_dy, float* __restrict__ grad_rec) {
     const int j = lane & (BKS - 1), h = lane >> 4;
     const float2* row = &sm.xw[warp][j][h * 16];
     const float4* dp = &sm.dpix[warp][h * 16];
     float m00 = 0.f, m10 = 0.f, m20 = 0.f, m01 = 0.f, m11 = 0.f, m02 = 0.f;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, cd = 0.f;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -272,6 +299,12 @@ __device__ __forceinline__ void bwd_flush(const RenderBwdSmem& sm, int warp, int
             c1 = fmaf(v.y, d.y, c1);
             c2 = fmaf(v.y, d.z, c2);
             cd = fmaf(v.y, d.w, cd);
+            if (AUX) {
+                const float4 e = sm.dpix_aux[warp][h * 16 + rr * 8 + x];
+                x0 = fmaf(v.y, e.x, x0);
+                x1 = fmaf(v.y, e.y, x1);
+                x2 = fmaf(v.y, e.z, x2);
+            }
         }
         const float yc = (float)(2 * h + rr) - 1.5f;
         m00 += r0; m10 += r1; m20 += r2;
@@ -284,6 +317,9 @@ __device__ __forceinline__ void bwd_flush(const RenderBwdSmem& sm, int warp, int
     m01 += __shfl_xor_sync(F, m01, 16); m11 += __shfl_xor_sync(F, m11, 16); m02 += __shfl_xor_sync(F, m02, 16);
     c0 += __shfl_xor_sync(F, c0, 16); c1 += __shfl_xor_sync(F, c1, 16);
     c2 += __shfl_xor_sync(F, c2, 16); cd += __shfl_xor_sync(F, cd, 16);
+    if (AUX) {
+        x0 += __shfl_xor_sync(F, x0, 16); x1 += __shfl_xor_sync(F, x1, 16); x2 += __shfl_xor_sync(F, x2, 16);
+    }
     if (j < ns) {
         const float4 ga = sm.slot_a[warp][j];
         const float4 gb = sm.slot_b[warp][j];
@@ -299,16 +335,19 @@ __device__ __forceinline__ void bwd_flush(const RenderBwdSmem& sm, int warp, int
         if (h == 0) {
             red_add_v4(g, o * ddelx_dx * (-ga.z * sx - ga.w * sy), o * ddely_dy * (-gb.x * sy - ga.w * sx), hf * sxx,
                        hf * sxy);
-            red_add_v2(g + 8, c2, cd);
+            if (AUX) red_add_v4(g + 8, c2, cd, x0, x1);
+            else red_add_v2(g + 8, c2, cd);
         } else {
             red_add_v4(g + 4, hf * syy, m00, c0, c1);
+            if (AUX) atomicAdd(g + 12, x2);
         }
     }
 }
 
+template <bool AUX>
 __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs a) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    RenderBwdSmem& sm = *reinterpret_cast<RenderBwdSmem*>(s_raw);
+    RenderBwdSmem<AUX>& sm = *reinterpret_cast<RenderBwdSmem<AUX>*>(s_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -336,8 +375,17 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
         dpixd = a.dL_dpix_depth[pix_id];
     }
     sm.dpix[warp][lane] = make_float4(dpix0, dpix1, dpix2, dpixd);
-    // -(T_final * sum_c bg_c dL/dpix_c): the background term of backward.cu:564-567
-    const float nbg = -T_final * (a.bg[0] * dpix0 + a.bg[1] * dpix1 + a.bg[2] * dpix2);
+    float dax0 = 0.f, dax1 = 0.f, dax2 = 0.f;
+    if (AUX) {
+        if (inside) {
+            dax0 = a.dL_dpix_aux[0 * HW + pix_id];
+            dax1 = a.dL_dpix_aux[1 * HW + pix_id];
+            dax2 = a.dL_dpix_aux[2 * HW + pix_id];
+        }
+        sm.dpix_aux[warp][lane] = make_float4(dax0, dax1, dax2, 0.f);
+    }
+    // -(T_final * sum_c bg_c dL/dpix_c): the background term of backward.cu:564-567 (both images share bg)
+    const float nbg = -T_final * (a.bg[0] * (dpix0 + dax0) + a.bg[1] * (dpix1 + dax1) + a.bg[2] * (dpix2 + dax2));
 
     // only instances below the block's deepest contributor matter (backward.cu:513)
     if (tid == 0) sm.max_contrib = 0;
@@ -366,6 +414,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
             cp_async16(&sm.rec[0][tid].a, &a.xyAB[id]);
             cp_async16(&sm.rec[0][tid].b, &a.Cod[id]);
             cp_async16(&sm.rec[0][tid].c, &a.rgb[id]);
+            if (AUX) cp_async16(&sm.aux[0][tid], &a.aux[id]);
         }
         cp_async_commit();
         const int i1 = m - 1 - (BCB + tid);
@@ -382,6 +431,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
                 cp_async16(&sm.rec[buf ^ 1][tid].a, &a.xyAB[id_next]);
                 cp_async16(&sm.rec[buf ^ 1][tid].b, &a.Cod[id_next]);
                 cp_async16(&sm.rec[buf ^ 1][tid].c, &a.rgb[id_next]);
+                if (AUX) cp_async16(&sm.aux[buf ^ 1][tid], &a.aux[id_next]);
             }
             const int i2 = m - 1 - ((b + 2) * BCB + tid);
             if (i2 >= 0) id_next = a.point_list[range.x + i2];
@@ -426,7 +476,11 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_kernel(RenderBwdArgs
                         T = T * inv;
                         w = alpha * T;
                         A = last_alpha * last_cd + (1.f - last_alpha) * A;
-                        const float cdv = col.x * dpix0 + col.y * dpix1 + col.z * dpix2 + col.w * dpixd;
+                        float cdv = col.x * dpix0 + col.y * dpix1 + col.z * dpix2 + col.w * dpixd;
+                        if (AUX) {
+                            const float4 ax = sm.aux[buf][jj];
+                            cdv += ax.x * dax0 + ax.y * dax1 + ax.z * dax2;
+                        }
                         last_cd = cdv;
                         last_alpha = alpha;
                         X = G * ((cdv - A) * T + nbg * inv);

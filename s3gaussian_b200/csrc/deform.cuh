@@ -323,7 +323,12 @@ __global__ void __launch_bounds__(256, 3) hexplane_sample_kernel(SampleArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int FL = FD * a.net.L;
-    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.P; g += gridDim.x * wpb) {
+    // Every block walks ONE contiguous run of Gaussians (its warps interleaved inside it): with the model kept in
+    // a spatially coherent order (GaussianModel.spatial_sort, Morton curve) a block keeps revisiting the same few
+    // texel lines while they are still in its SM's L1; in arbitrary order the assignment makes no difference.
+    const int chunk = (a.P + gridDim.x - 1) / gridDim.x;
+    const int g_begin = blockIdx.x * chunk, g_end = min(a.P, g_begin + chunk);
+    for (int g = g_begin + (threadIdx.x >> 5); g < g_end; g += wpb) {
         float ph[4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)g * 3 + c) - a.net.aabb0[c]) * a.net.inv_span2[c] - 1.0f;
@@ -996,7 +1001,9 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int FL = FD * L;
-    for (int gi = blockIdx.x * wpb + (threadIdx.x >> 5); gi < a.P; gi += gridDim.x * wpb) {
+    const int chunk = (a.P + gridDim.x - 1) / gridDim.x;      // contiguous run per block, see hexplane_sample_kernel
+    const int g_begin = blockIdx.x * chunk, g_end = min(a.P, g_begin + chunk);
+    for (int gi = g_begin + (threadIdx.x >> 5); gi < g_end; gi += wpb) {
         float ph[4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gi * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;

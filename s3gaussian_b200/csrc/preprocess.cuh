@@ -186,6 +186,7 @@ struct PreFwdArgs {
     const float* shs;
     const float* cov3D_precomp;
     const float* colors_precomp;
+    const float* colors_aux;   // [P,3] second colour set (feature image of render_feat) or NULL
     const float* view;
     const float* proj;
     const float* campos;
@@ -195,6 +196,7 @@ struct PreFwdArgs {
     float4* xyAB;
     float4* Cod;
     float4* rgb;
+    float4* aux;
     uint32_t* depth_key;
     uint32_t* tiles_touched;
     ushort4* rect;
@@ -379,6 +381,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(PreFwdA
                              cull_tau(opacity, po.conic.x, po.conic.y, po.conic.z, po.lam_max, po.lam_min),
                              __uint_as_float((uint32_t)idx));
     a.rgb[idx] = make_float4(col.x, col.y, col.z, po.depth);
+    if (a.colors_aux)
+        a.aux[idx] = make_float4(a.colors_aux[3 * idx], a.colors_aux[3 * idx + 1], a.colors_aux[3 * idx + 2], 0.f);
     a.rect[idx] = make_ushort4((unsigned short)po.rminx, (unsigned short)po.rminy, (unsigned short)po.rmaxx,
                                (unsigned short)po.rmaxy);
     a.tiles_touched[idx] = (po.rmaxy - po.rminy) * (po.rmaxx - po.rminx);
@@ -419,6 +423,7 @@ struct PreBwdArgs {
     float* dL_dconic;        // [P,4] or NULL
     float* dL_dopacity;      // [P]
     float* dL_dcolor;        // [P,3]
+    float* dL_dcolor_aux;    // [P,3] or NULL
     float* dL_ddepth;        // [P] or NULL
     float* dL_dmean3D;       // [P,3]
     float* dL_dcov3D;        // [P,6]
@@ -489,6 +494,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(PreBwd
     a.dL_dcolor[3 * idx + 1] = g[7];
     a.dL_dcolor[3 * idx + 2] = g[8];
     if (a.dL_ddepth) a.dL_ddepth[idx] = g[9];
+    if (a.dL_dcolor_aux) {
+        a.dL_dcolor_aux[3 * idx + 0] = g[10];
+        a.dL_dcolor_aux[3 * idx + 1] = g[11];
+        a.dL_dcolor_aux[3 * idx + 2] = g[12];
+    }
     }
 
     float dmean[3] = {0.f, 0.f, 0.f};

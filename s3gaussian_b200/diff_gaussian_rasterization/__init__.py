@@ -132,10 +132,18 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                                      rotations, cov3Ds_precomp, raster_settings)
 
 
+def rasterize_gaussians_aux(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                            cov3Ds_precomp, raster_settings, colors_aux):
+    """(color, radii, depth, color_aux): both colour sets composited on ONE preprocess + sort
+    (s3g_rasterize_forward_aux / s3g_rasterize_backward_aux)."""
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings, colors_aux)
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings):
+                cov3Ds_precomp, raster_settings, colors_aux=None):
         lib = _lib.load()
         if means3D.dim() != 2 or means3D.size(1) != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
@@ -153,6 +161,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         scales = _f32c(scales, dev)
         rotations = _f32c(rotations, dev)
         cov3Ds_precomp = _f32c(cov3Ds_precomp, dev)
+        has_aux = colors_aux is not None
+        if has_aux:
+            colors_aux = _f32c(colors_aux, dev)
+            if tuple(colors_aux.shape) != (P, 3):
+                raise RuntimeError("colors_aux must have dimensions (num_points, 3)")
         bg = _f32c(rs.bg, dev)
         view = _f32c(rs.viewmatrix, dev)
         proj = _f32c(rs.projmatrix, dev)
@@ -161,6 +174,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        color_aux = torch.empty((3, H, W), dtype=torch.float32, device=dev) if has_aux else None
         lease = _Lease(dev)
         geom, binning, img = lease.aset.geom, lease.aset.binning, lease.aset.img
         M = sh.size(1) if sh.numel() != 0 else 0
@@ -171,6 +185,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                 int(bool(rs.prefiltered)), color.data_ptr(), depth.data_ptr(), _ptr(radii),
                 int(bool(rs.debug)), _stream_ptr(dev))
+        fwd = lib.s3g_rasterize_forward
+        if has_aux:
+            args = args + (_ptr(colors_aux), color_aux.data_ptr())
+            fwd = lib.s3g_rasterize_forward_aux
         with torch.cuda.device(dev):
             if rs.debug:
                 cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, colors_precomp, opacities, scales,
@@ -179,13 +197,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                                                 rs.image_height, rs.image_width, sh, rs.sh_degree,
                                                 rs.campos, rs.prefiltered, rs.debug))
                 try:
-                    num_rendered = _lib.check(lib.s3g_rasterize_forward(*args), "rasterize_gaussians")
+                    num_rendered = _lib.check(fwd(*args), "rasterize_gaussians")
                 except Exception as ex:
                     torch.save(cpu_args, "snapshot_fw.dump")
                     print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                     raise ex
             else:
-                num_rendered = _lib.check(lib.s3g_rasterize_forward(*args), "rasterize_gaussians")
+                num_rendered = _lib.check(fwd(*args), "rasterize_gaussians")
 
         ctx.raster_settings = rs
         ctx.num_rendered = int(num_rendered)
@@ -196,10 +214,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh,
                               geom.tensor, binning.tensor, img.tensor)
         ctx.mark_non_differentiable(radii)
+        ctx.has_aux = has_aux
+        if has_aux:
+            return color, radii, depth, color_aux
         return color, radii, depth
 
     @staticmethod
-    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+    def backward(ctx, grad_out_color, grad_radii, grad_depth, grad_out_aux=None):
         lib = _lib.load()
         rs = ctx.raster_settings
         (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
@@ -233,6 +254,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_colors, grad_opacities = e("colors_precomp", P, 3), e("opacities", P, 1)
         grad_cov3D, grad_sh = e("cov3D_precomp", P, 6), e("shs", P, M, 3)
         grad_scales, grad_rotations = e("scales", P, 3), e("rotations", P, 4)
+        grad_aux = None
+        if ctx.has_aux:
+            if grad_out_aux is None:
+                grad_out_aux = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+            grad_out_aux = _f32c(grad_out_aux, dev)
+            grad_aux = e("colors_aux", P, 3)
 
         args = (P, int(rs.sh_degree), M, ctx.num_rendered, _ptr(bg), W, H, _ptr(means3D), _ptr(sh),
                 _ptr(colors_precomp), _ptr(scales), float(rs.scale_modifier), _ptr(rotations),
@@ -242,16 +269,20 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(grad_means2D), None, _ptr(grad_opacities), _ptr(grad_colors), None,
                 _ptr(grad_means3D), _ptr(grad_cov3D), _ptr(grad_sh), _ptr(grad_scales),
                 _ptr(grad_rotations), int(bool(rs.debug)), _stream_ptr(dev))
+        bwd = lib.s3g_rasterize_backward
+        if ctx.has_aux:
+            args = args + (grad_out_aux.data_ptr(), grad_aux.data_ptr())
+            bwd = lib.s3g_rasterize_backward_aux
         with torch.cuda.device(dev):
             if P > 0:
                 if rs.debug:
                     try:
-                        _lib.check(lib.s3g_rasterize_backward(*args), "rasterize_gaussians_backward")
+                        _lib.check(bwd(*args), "rasterize_gaussians_backward")
                     except Exception as ex:
                         print("\nAn error occured in backward.\n")
                         raise ex
                 else:
-                    _lib.check(lib.s3g_rasterize_backward(*args), "rasterize_gaussians_backward")
+                    _lib.check(bwd(*args), "rasterize_gaussians_backward")
 
         has_colors = colors_precomp.numel() != 0
         has_cov = cov3Ds_precomp.numel() != 0
@@ -266,6 +297,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_cov3D if has_cov else None,
             None,
         )
+        if ctx.has_aux:
+            grads = grads + (grad_aux,)
         return grads
 
 
@@ -330,3 +363,20 @@ class GaussianRasterizer(nn.Module):
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
                                    rotations, cov3D_precomp, raster_settings)
+
+    def forward_aux(self, means3D, means2D, opacities, colors_aux, shs=None, colors_precomp=None, scales=None,
+                    rotations=None, cov3D_precomp=None):
+        """forward() plus a second [P,3] colour set composited on the same binning:
+        -> (color, radii, depth, color_aux).  Not in the reference (it calls forward() twice,
+        gaussian_renderer/__init__.py:173-186); same arguments otherwise."""
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        E = torch.Tensor([])
+        return rasterize_gaussians_aux(means3D, means2D, shs if shs is not None else E,
+                                       colors_precomp if colors_precomp is not None else E, opacities,
+                                       scales if scales is not None else E, rotations if rotations is not None else E,
+                                       cov3D_precomp if cov3D_precomp is not None else E, self.raster_settings,
+                                       colors_aux)

@@ -73,6 +73,11 @@ class PipelineParams:       # arguments/__init__.py:93-98 defaults
     convert_SHs_python = True
     compute_cov3D_python = False
     debug = False
+    shared_binning = True   # ours: colour + feature image in one rasterizer pass (False = two passes, as upstream)
+
+
+def pipe_shared_binning(pipe) -> bool:
+    return bool(getattr(pipe, "shared_binning", True))
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
@@ -146,17 +151,27 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     if override_color is not None:
         colors_precomp, shs_final = override_color, None
 
-    rendered_image, radii, depth = rasterizer(
-        means3D=means3D_final, means2D=means2D, shs=shs_final, colors_precomp=colors_precomp, opacities=opacity,
-        scales=scales_final, rotations=rotations_final, cov3D_precomp=cov3D_precomp)
+    want_feat = render_feat and "fine" in stage and feat is not None
+    rendered_image2 = None
+    if want_feat and hasattr(rasterizer, "forward_aux") and pipe_shared_binning(pipe):
+        # the feature image shares preprocess, sort and the per-pixel alpha evaluation with the colour image
+        # (the reference rasterizes the same geometry a second time, gaussian_renderer/__init__.py:173-186)
+        rendered_image, radii, depth, rendered_image2 = rasterizer.forward_aux(
+            means3D=means3D_final, means2D=means2D, opacities=opacity, colors_aux=feat, shs=shs_final,
+            colors_precomp=colors_precomp, scales=scales_final, rotations=rotations_final, cov3D_precomp=cov3D_precomp)
+    else:
+        rendered_image, radii, depth = rasterizer(
+            means3D=means3D_final, means2D=means2D, shs=shs_final, colors_precomp=colors_precomp, opacities=opacity,
+            scales=scales_final, rotations=rotations_final, cov3D_precomp=cov3D_precomp)
 
     result_dict = {"render": rendered_image, "viewspace_points": screenspace_points,
                    "visibility_filter": radii > 0, "radii": radii, "depth": depth}
 
-    if render_feat and "fine" in stage and feat is not None:
-        rendered_image2, _, _ = rasterizer(
-            means3D=means3D_final, means2D=means2D, shs=None, colors_precomp=feat, opacities=opacity,
-            scales=scales_final, rotations=rotations_final, cov3D_precomp=cov3D_precomp)
+    if want_feat:
+        if rendered_image2 is None:
+            rendered_image2, _, _ = rasterizer(
+                means3D=means3D_final, means2D=means2D, shs=None, colors_precomp=feat, opacities=opacity,
+                scales=scales_final, rotations=rotations_final, cov3D_precomp=cov3D_precomp)
         result_dict.update({"feat": rendered_image2})
 
     if return_decomposition and dx is not None:

@@ -380,3 +380,48 @@ def test_binning_capacity_overflow_is_repeated_not_truncated(ours, oracle_lib):
                                              ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
         assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
         assert util.relerr(depth.cpu().numpy(), o["depth"]) < TOL
+
+
+def test_shared_binning_two_colour_sets_equal_two_passes(ours):
+    """forward_aux / s3g_rasterize_*_aux: colour image + feature image composited on one preprocess + sort must equal
+    two full passes (what gaussian_renderer/__init__.py:173-186 does) - images, and the gradients of the SUM of both
+    losses w.r.t. geometry, opacity and both colour sets; against our own two passes and the reference's."""
+    from s3gaussian_b200 import synthetic as syn
+    P, W, H = 60_000, 640, 416
+    cloud = syn.make_cloud(P, seed=4, width=W, height=H)
+    cam = syn.make_camera(W, H, (0, 0, 2.0))
+    d = util.scene_inputs(cloud, cam, mode="rgb", bg=(0.3, 0.1, 0.2))
+    g = torch.Generator().manual_seed(8)
+    feat = torch.rand(P, 3, generator=g)
+    gc, gd = util.seeded_grads(d, 21)
+    gf = torch.randn(3, H, W, generator=g)
+
+    def run(mod, fused):
+        t = {k: d[k].to(DEV).clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp")}
+        fa = feat.to(DEV).clone().requires_grad_(True)
+        m2d = torch.zeros_like(t["means3D"], requires_grad=True)
+        rast = mod.GaussianRasterizer(util.settings_for(mod, d, DEV))
+        kw = dict(means3D=t["means3D"], means2D=m2d, opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"])
+        if fused:
+            color, radii, depth, aux = rast.forward_aux(colors_aux=fa, colors_precomp=t["colors_precomp"], **kw)
+        else:
+            color, radii, depth = rast(colors_precomp=t["colors_precomp"], **kw)
+            aux, _, _ = rast(colors_precomp=fa, **kw)
+        ((color * gc.to(DEV)).sum() + (depth * gd.to(DEV)).sum() + (aux * gf.to(DEV)).sum()).backward()
+        grads = {k: v.grad.detach() for k, v in t.items()}
+        grads["colors_aux"], grads["means2D"] = fa.grad.detach(), m2d.grad.detach()
+        return color.detach(), depth.detach(), aux.detach(), radii, grads
+    c1, d1, a1, r1, g1 = run(ours, True)
+    c2, d2, a2, r2, g2 = run(ours, False)
+    assert torch.equal(r1, r2) and torch.equal(c1, c2) and torch.equal(d1, d2)
+    assert util.relerr(a1.cpu().numpy(), a2.cpu().numpy()) < 1e-6
+    for k in g2:
+        e = util.relerr(g1[k].cpu().numpy(), g2[k].cpu().numpy())
+        assert e < 2e-5, (k, e)
+    if ref_ext.available():
+        c3, d3, a3, r3, g3 = run(ref_ext.load(), False)
+        assert torch.equal(r1, r3)
+        assert util.relerr(a1.cpu().numpy(), a3.cpu().numpy()) < TOL
+        for k in g3:
+            e = util.relerr(g1[k].cpu().numpy(), g3[k].cpu().numpy())
+            assert e < TOL, (k, e)

@@ -385,13 +385,21 @@ def main():
     if world > 1:
         comm_ms = None
         if comm_ev is not None:
-            step_resident()
-            torch.cuda.synchronize()
-            comm_ms = round(comm_ev[0].elapsed_time(comm_ev[1]), 4)
+            # ranks aligned at the start of the measured step: comm_ms = this rank's wait for the slowest view +
+            # the collective itself (the event pair brackets the all-reduce on this rank's stream)
+            vals = []
+            for _ in range(5):
+                torch.cuda.synchronize()
+                dist.barrier()
+                step_resident()
+                torch.cuda.synchronize()
+                vals.append(comm_ev[0].elapsed_time(comm_ev[1]))
+            comm_ms = round(float(np.median(vals)), 4)
         mine = {"rank": rank, "step_ms": round(ms_res_local / a.steps, 4), "comm_ms": comm_ms, "visible": V,
                 "num_rendered": R,
                 "render_ms": (round(sum(stages["forward_ms"].values()) + sum(stages["backward_ms"].values()), 4)
-                              if stages else None)}
+                              if stages else None),
+                "stages": stages}
         if bucket is not None:
             o, n = offs["means3D"]
             mine["sink_aliased"] = bool(t["means3D"].grad is not None and t["means3D"].grad.data_ptr() == bucket[o:o + n].data_ptr())

@@ -310,9 +310,6 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
  * D[128,N] = A[128,K] * B[N,K]^T on the 5th-gen tensor cores (kind::tf32, accumulators in TMEM),
  * single pass or 3xTF32.  K % 8 == 0, K <= 128, N % 16 == 0, N <= 64.  Device pointers. */
 int s3g_umma_selftest(const float* A, const float* B, float* D, int K, int N, int three_pass, void* stream);
-/* D[128,N] = A[128,128]^T * B[128,N] through MN-major operand descriptors (the layout the weight-gradient
- * products of a tcgen05 backward decoder need).  Building block for round 2. */
-int s3g_umma_selftest_mn(const float* A, const float* B, float* D, int N, int three_pass, void* stream);
 
 /* ---- per-stage device timing (bench.py roofline leg) ----------------------
  * When enabled, forward/backward bracket every kernel stage with cudaEvents on

@@ -45,7 +45,6 @@ SIGNATURES = {
     "s3g_deform_workspace_bytes": (_SZ, [_V, _I]),
     "s3g_deform_backward": (_I, [_V, _I] + [_V] * 5 + [_F, _V, _I] + [_V] + [_V] * 8 + [_V] * 5 + [_V, _V, _V]),
     "s3g_umma_selftest": (_I, [_V, _V, _V, _I, _I, _I, _V]),
-    "s3g_umma_selftest_mn": (_I, [_V, _V, _V, _I, _I, _V]),
     "s3g_profile_enable": (_I, [_I]),
     "s3g_profile_read": (_I, [_I, _V, _I]),
     "s3g_profile_stage_name": (C.c_char_p, [_I, _I]),

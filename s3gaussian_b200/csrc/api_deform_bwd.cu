@@ -27,8 +27,6 @@ int bwd_grid(int ntiles) {
 }
 constexpr int kMaxBwdGrid = 256;
 
-// ---- tcgen05 backward decoder (DRAFT, own translation unit api_deform_tc_bwd.cu): only with S3G_TC_BWD=1 -----
-constexpr size_t kTcBwdPrepFloats = (size_t)14 * 2 * 64 * 64;     // prepared weights of the draft (14 entries <= 64 x 64, hi + lo)
 }  // namespace
 
 extern "C" {
@@ -39,8 +37,7 @@ size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
     GradOff o;
     make_offsets(d, o);
     // per-CTA partial Linear gradients + dL/d(features) [P][32L]
-    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float) +
-           kTcBwdPrepFloats * sizeof(float) + 256;
+    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float) + 256;
 }
 
 int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
@@ -105,12 +102,7 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
     if (P > 0) {
         const size_t smem = DeformBwdSmem::floats(d.L) * sizeof(float);
         if (smem > 227 * 1024) return fail(S3G_ERR_UNSUPPORTED, "deform_backward: too many levels for shared memory");
-        int tgrid = 0;
-        if (tc_bwd_launch(a, kMaxBwdGrid, stream, &tgrid)) {       // DRAFT path, see api_deform_tc_bwd.cu
-            if (tgrid < 0) return tgrid;
-            grid = tgrid;
-            r.nparts = tgrid;
-        } else if (d.L == 4) {
+        if (d.L == 4) {
             S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
             deform_backward_kernel<4><<<grid, DTHREADS, smem, stream>>>(a);
         } else {

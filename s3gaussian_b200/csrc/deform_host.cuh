@@ -72,8 +72,4 @@ inline void build_wseq(const DNet& d, bool backward, WSeq& q) {
     if (backward) add(d.w_feat, 64, KF);
 }
 
-// api_deform_tc_bwd.cu: launches the tcgen05 backward decoder DRAFT when S3G_TC_BWD=1 and the configuration is
-// supported.  Returns false when the caller should use the mma.sync kernel; *grid_out = CTAs launched (= partial
-// buffers to reduce) or a negative S3G_ERR_* code.
-bool tc_bwd_launch(const DeformBwdArgs& a, int max_grid, cudaStream_t stream, int* grid_out);
 }  // namespace s3g

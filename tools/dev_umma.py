@@ -19,21 +19,6 @@ for K, N in [(64, 64), (128, 64), (64, 48), (64, 16), (8, 16), (128, 32)]:
         ok &= (err < (2e-6 if three else 3e-3))
 print("UMMA SELFTEST", "OK" if ok else "FAILED")
 
-if "--mn" in sys.argv:
-    # MN-major operands (round-2 building block): D = A^T B with the reduction over the 128 rows
-    ok = True
-    for N in (16, 32, 64):
-        A = torch.randn(128, 128, device=dev, generator=g); B = torch.randn(128, N, device=dev, generator=g)
-        ref = A.double().t() @ B.double()
-        for three in (0, 1):
-            D = torch.full((128, N), float("nan"), device=dev)
-            rc = lib.s3g_umma_selftest_mn(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, three, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            torch.cuda.synchronize()
-            err = float((D.double() - ref).abs().max() / ref.abs().max())
-            print(f"MN-major N={N} three_pass={three} rc={rc} rel err {err:.3e}")
-            ok &= (err < (2e-6 if three else 3e-3))
-    print("UMMA MN-MAJOR SELFTEST", "OK" if ok else "FAILED")
-
 if "--probe" in sys.argv:
     # Descriptor probe (csrc/umma_probe.cu): which shared-memory word does the tensor core read as A(m, k) / B(n, k)
     # for a given (major-ness, layout type, LBO, SBO)?  The other operand is a K-major identity, the probed operand's

@@ -61,6 +61,10 @@ def parse():
                     help="N > 1: force ncclAllReduce for the gradient bucket")
     ap.add_argument("--peer-allreduce", action="store_true",
                     help="N > 1: force the peer-memory reduce-scatter/all-gather kernels (default at N <= 3)")
+    ap.add_argument("--fused-exchange", action="store_true",
+                    help="N > 1: fuse the first half of the gradient exchange into the backward kernel "
+                         "(dp.FusedGradExchange).  Measured slower than the stand-alone all-reduce at N = 2 "
+                         "(3.75 vs 3.36 ms/step, profiles/r02e_*), so it is opt-in")
     ap.add_argument("--no-train-iteration", action="store_true",
                     help="skip the whole-training-iteration leg (render + loss + stats + Adam, N == 1 only)")
     ap.add_argument("--cpu-sample", type=int, default=500_000)
@@ -193,7 +197,18 @@ def main():
     peer, peer_why = None, None
     # measured on the 8-GPU box (profiles/r01h_*): the peer kernels beat NCCL at 2 GPUs (0.75 vs 0.89 ms for
     # 472 MB), NCCL's in-switch (NVLS) reduction wins at 8 (1.18 vs 1.48 ms); default accordingly
-    use_peer = a.peer_allreduce or (world <= 3 and not a.nccl_allreduce)
+    # opt-in: the exchange fused into the backward kernel (visible rows stored straight into the owner rank's
+    # staging over NVLink, one reduce + multicast-gather kernel afterwards)
+    fused = None
+    if world > 1 and a.impl == "ours" and a.mode == "sh" and a.fused_exchange and not (a.nccl_allreduce or a.peer_allreduce):
+        from s3gaussian_b200 import dp
+        fused, fused_why = dp.make_fused_grad_exchange(
+            {"means3D": (P, 3), "shs": (P, 16, 3), "opacities": (P, 1), "scales": (P, 3), "rotations": (P, 4)}, dev)
+        agree = torch.tensor([1 if fused is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree[0]) == 0:
+            fused = None
+    use_peer = fused is None and (a.peer_allreduce or (world <= 3 and not a.nccl_allreduce))
     if world > 1 and a.impl == "ours" and use_peer:
         from s3gaussian_b200 import dp
         n_grad = sum(v.numel() for v in leaves if v is not m2d)
@@ -207,7 +222,12 @@ def main():
     # the communication bucket (symmetric memory for the peer kernels, a plain flat tensor for NCCL) - no gather copy
     # between the backward and the collective.  The reference arm keeps torch.cat + ncclAllReduce.
     bucket, comm_ev = None, None
-    if world > 1 and a.impl == "ours":
+    if fused is not None:
+        fused.install()
+        bucket = fused.bucket
+        offs = {k: (o, c) for k, (o, c, _s) in fused.offsets.items()}
+        comm_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    elif world > 1 and a.impl == "ours":
         names = {"means3D": t["means3D"], "shs": t["shs"], "colors_precomp": t["colors_precomp"],
                  "opacities": t["opacities"], "scales": t["scales"], "rotations": t["rotations"]}
         offs, n_tot = {}, 0
@@ -229,7 +249,9 @@ def main():
         if world > 1:
             if bucket is not None:
                 comm_ev[0].record()
-                if peer is not None:
+                if fused is not None:
+                    fused.finish()
+                elif peer is not None:
                     peer.all_reduce_()
                 else:
                     dist.all_reduce(bucket)
@@ -503,7 +525,10 @@ def main():
         "config": {"workload": f"{P} Gaussians ({'SH deg 3 in-kernel' if a.mode == 'sh' else 'precomputed colours'}), "
                                f"{W}x{H}, 1 view/GPU of the 50-frame ring, rasterizer fwd+bwd"
                                + (", all-reduce of per-Gaussian grads" if world > 1 else ""),
-                   "collective": (("NVLink peer-memory reduce-scatter/all-gather kernels (csrc/peer.cuh)" if peer is not None
+                   "collective": (("fused: backward kernel stores visible rows into the owner rank's staging over NVLink, "
+                                   "then one reduce + " + ("multimem.st" if fused.mc else "peer-store") + " gather kernel "
+                                   "(dp.FusedGradExchange)") if fused is not None else
+                                  ("NVLink peer-memory reduce-scatter/all-gather kernels (csrc/peer.cuh)" if peer is not None
                                    else "ncclAllReduce") if world > 1 else None),
                    "points": P, "width": W, "height": H, "visible": V, "num_rendered": R,
                    "parallelism": f"view-parallel dp{world}",

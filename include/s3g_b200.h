@@ -145,6 +145,58 @@ int s3g_rasterize_backward(
     int debug,
     void* stream);
 
+/* ---- backward fused with the first half of the data-parallel gradient exchange ----------------------------------
+ * View-parallel training (one camera per GPU, replicated Gaussians; reference batch loop train.py:372-392) sums the
+ * per-Gaussian gradients over the ranks every step.  With a peer sink the backward's last kernel does not write
+ * dL_dmean3D / dL_dsh / dL_dopacity / dL_dscale / dL_drot locally: every VISIBLE Gaussian's values are stored over
+ * NVLink straight into the staging area of the rank that owns that slice of the flat gradient bucket
+ * (stage[o] = rank o's area, laid out [world][chunk] floats, pre-zeroed; element e of the bucket lives in slice
+ * e / chunk).  s3g_peer_reduce_gather() on every rank then sums its `world` sub-slices in rank order, stores the sums
+ * into every rank's bucket (multimem.st through the multicast mapping, or peer stores) and re-zeroes the staging.
+ * The five pointers named above may be NULL; everything else is as in s3g_rasterize_backward.  The caller provides
+ * the two device-side barriers (all ranks: backward_dp | barrier | reduce_gather | barrier).  off_* are float
+ * offsets of the tensors inside the bucket (off_shs % 4 == 0; off_shs ignored with colors_precomp). */
+typedef struct s3g_peer_sink {
+    int world, rank;
+    int64_t chunk;                 /* floats per owner slice, multiple of 4, world * chunk >= bucket size */
+    void* stage[16];               /* peer-mapped staging base of every rank */
+    int64_t off_means3D, off_shs, off_opacities, off_scales, off_rotations;
+} s3g_peer_sink;
+int s3g_rasterize_backward_dp(
+    int P, int D, int M, int64_t R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer,
+    char* binning_buffer,
+    char* image_buffer,
+    const float* dL_dpix,
+    const float* dL_dpix_depth,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_ddepth,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    int debug,
+    void* stream,
+    const s3g_peer_sink* sink);
+
 /* ---- one binning, two colour sets -------------------------------------------------
  * render(render_feat=True) rasterizes the same Gaussians twice - once with the RGB colours, once with the
  * three-channel feature colours (gaussian_renderer/__init__.py:173-186, train.py:373) - and the reference runs its
@@ -432,6 +484,10 @@ int s3g_peer_all_gather(int world, int rank, const void* const* bufs, int64_t nu
 /* NVLS variant: one kernel on the MULTICAST address of the same symmetric buffer (multimem.ld_reduce +
  * multimem.st on slice `rank`), barriers before and after as above.  Written for round 2, not yet measured. */
 int s3g_peer_nvls_all_reduce(int world, int rank, void* multicast_ptr, int64_t numel, void* stream);
+/* second half of the exchange started by s3g_rasterize_backward_dp: stage_local = this rank's staging
+ * [world][chunk]; results go to bucket_multicast (multimem.st) when non-NULL, else to bucket_ptrs[0..world-1]. */
+int s3g_peer_reduce_gather(int world, int rank, void* stage_local, const void* const* bucket_ptrs,
+                           void* bucket_multicast, int64_t numel, int64_t chunk, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,10 @@ SIGNATURES = {
     "s3g_rasterize_backward_aux": (_I, [_I, _I, _I, _I64, _V, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V,
                                         _V, _F, _F, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
                                         _V, _V, _V, _I, _V, _V, _V]),
+    "s3g_rasterize_backward_dp": (_I, [_I, _I, _I, _I64, _V, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V,
+                                       _V, _F, _F, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V,
+                                       _V, _V, _V, _I, _V, _V]),
+    "s3g_peer_reduce_gather": (_I, [_I, _I, _V, _V, _V, _I64, _I64, _V]),
     "s3g_state_field": (_I, [_I, C.c_char_p, _I64, _I64, _I, _I, C.POINTER(_SZ), C.POINTER(_SZ),
                              C.POINTER(_SZ)]),
     # struct pointers (s3g_deform_net / s3g_deform_net_grads) are passed with ctypes.byref()
@@ -125,6 +129,13 @@ def profile_read(which: int) -> dict:
     buf = (C.c_float * 16)()
     n = check(lib.s3g_profile_read(which, buf, 16), "s3g_profile_read")
     return {lib.s3g_profile_stage_name(which, i).decode(): float(buf[i]) for i in range(n)}
+
+
+class PeerSink(C.Structure):
+    """s3g_peer_sink (include/s3g_b200.h)."""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("chunk", C.c_int64), ("stage", C.c_void_p * 16),
+                ("off_means3D", C.c_int64), ("off_shs", C.c_int64), ("off_opacities", C.c_int64),
+                ("off_scales", C.c_int64), ("off_rotations", C.c_int64)]
 
 
 class PlaneDesc(C.Structure):

@@ -443,7 +443,8 @@ int backward_impl(int P, int D, int M, int64_t R, const float* background, int w
                            const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
                            float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
                            float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-                           int debug, void* stream_, const float* dL_dpix_aux, float* dL_dcolor_aux) {
+                           int debug, void* stream_, const float* dL_dpix_aux, float* dL_dcolor_aux,
+                           const s3g_peer_sink* sink = nullptr) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(S3G_ERR_ARG, "backward: bad sizes");
     if (P == 0) return S3G_OK;   // rasterize_points.cu:165
@@ -451,14 +452,23 @@ int backward_impl(int P, int D, int M, int64_t R, const float* background, int w
         return fail(S3G_ERR_STATE, "backward: missing state buffer");
     if (!means3D || !viewmatrix || !projmatrix || !background || !dL_dpix || !dL_dpix_depth)
         return fail(S3G_ERR_ARG, "backward: null input");
-    if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
-        !dL_drot)
+    if (!sink && (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot))
         return fail(S3G_ERR_ARG, "backward: null gradient output");
+    if (sink) {
+        if (!dL_dmean2D || !dL_dcolor) return fail(S3G_ERR_ARG, "backward_dp: dL_dmean2D / dL_dcolor stay local and must be given");
+        if (cov3D_precomp) return fail(S3G_ERR_ARG, "backward_dp: precomputed 3-D covariances are not exchanged");
+        if (sink->world < 2 || sink->world > 16 || sink->rank < 0 || sink->rank >= sink->world || sink->chunk <= 0 ||
+            (sink->chunk & 3) || sink->off_means3D < 0 || sink->off_opacities < 0 || sink->off_scales < 0 ||
+            sink->off_rotations < 0 || (colors_precomp == nullptr && (sink->off_shs < 0 || (sink->off_shs & 3))))
+            return fail(S3G_ERR_ARG, "backward_dp: bad peer sink (world, rank, chunk % 4, offsets, off_shs % 4)");
+        for (int p = 0; p < sink->world; ++p)
+            if (!sink->stage[p]) return fail(S3G_ERR_ARG, "backward_dp: null staging pointer");
+    }
     if ((dL_dpix_aux != nullptr) != (dL_dcolor_aux != nullptr))
         return fail(S3G_ERR_ARG, "backward: dL_dpix_aux and dL_dcolor_aux go together");
     const bool use_aux = dL_dpix_aux != nullptr;
     const bool use_sh = (colors_precomp == nullptr);
-    if (use_sh && (!shs || !dL_dsh || !campos)) return fail(S3G_ERR_ARG, "backward: SH path needs shs, dL_dsh, campos");
+    if (use_sh && (!shs || (!dL_dsh && !sink) || !campos)) return fail(S3G_ERR_ARG, "backward: SH path needs shs, dL_dsh, campos");
     if (!cov3D_precomp && (!scales || !rotations))
         return fail(S3G_ERR_ARG, "backward: need scales+rotations or precomputed cov3D");
 
@@ -518,11 +528,27 @@ int backward_impl(int P, int D, int M, int64_t R, const float* background, int w
     pb.dL_dcolor = dL_dcolor; pb.dL_dcolor_aux = dL_dcolor_aux; pb.dL_ddepth = dL_ddepth; pb.dL_dmean3D = dL_dmean3D;
     pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = use_sh ? dL_dsh : nullptr;
     pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot;
+    if (sink) {
+        for (int p = 0; p < 16; ++p) pb.sink.stage[p] = p < sink->world ? static_cast<float*>(sink->stage[p]) : nullptr;
+        pb.sink.world = sink->world; pb.sink.rank = sink->rank; pb.sink.chunk = sink->chunk;
+        pb.sink.off_mean3D = sink->off_means3D; pb.sink.off_sh = sink->off_shs; pb.sink.off_opacity = sink->off_opacities;
+        pb.sink.off_scale = sink->off_scales; pb.sink.off_rot = sink->off_rotations;
+    }
     {
         const size_t smem = use_sh ? (size_t)(PRE_THREADS / 32) * 32 * row_stride(3 * M) * sizeof(float) : 0;
         if (smem > 200 * 1024) return fail(S3G_ERR_ARG, "backward: too many SH coefficients");
         const int grid = (P + PRE_THREADS - 1) / PRE_THREADS;
-        if (use_sh && M == 16) {
+        if (sink) {
+            if (use_sh && M == 16) {
+                preprocess_backward_kernel<16, true><<<grid, PRE_THREADS, smem, stream>>>(pb);
+            } else {
+                if (smem > 48 * 1024)
+                    S3G_CUDA(cudaFuncSetAttribute(preprocess_backward_kernel<0, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                             "smem attribute");
+                preprocess_backward_kernel<0, true><<<grid, PRE_THREADS, smem, stream>>>(pb);
+            }
+        } else if (use_sh && M == 16) {
             preprocess_backward_kernel<16><<<grid, PRE_THREADS, smem, stream>>>(pb);
         } else {
             if (smem > 48 * 1024)
@@ -588,6 +614,25 @@ int s3g_rasterize_backward(int P, int D, int M, int64_t R, const float* backgrou
                          binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity,
                          dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream, nullptr,
                          nullptr);
+}
+
+int s3g_rasterize_backward_dp(int P, int D, int M, int64_t R, const float* background, int width,
+                              int height, const float* means3D, const float* shs,
+                              const float* colors_precomp, const float* scales, float scale_modifier,
+                              const float* rotations, const float* cov3D_precomp,
+                              const float* viewmatrix, const float* projmatrix, const float* campos,
+                              float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                              char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                              const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic,
+                              float* dL_dopacity, float* dL_dcolor, float* dL_ddepth, float* dL_dmean3D,
+                              float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                              int debug, void* stream, const s3g_peer_sink* sink) {
+    if (!sink) return fail(S3G_ERR_ARG, "backward_dp: null sink");
+    return backward_impl(P, D, M, R, background, width, height, means3D, shs, colors_precomp, scales, scale_modifier,
+                         rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                         binning_buffer, image_buffer, dL_dpix, dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity,
+                         dL_dcolor, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, stream, nullptr,
+                         nullptr, sink);
 }
 
 int s3g_rasterize_backward_aux(int P, int D, int M, int64_t R, const float* background, int width,

@@ -70,4 +70,36 @@ int s3g_peer_nvls_all_reduce(int world, int rank, void* multicast_ptr, int64_t n
     return S3G_OK;
 }
 
+int s3g_peer_reduce_gather(int world, int rank, void* stage_local, const void* const* bucket_ptrs,
+                           void* bucket_multicast, int64_t numel, int64_t chunk, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (world < 2 || world > PEER_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(S3G_ERR_ARG, "peer: 2 <= world <= 16, 0 <= rank < world");
+    if (!stage_local || ((uintptr_t)stage_local & 15) || numel <= 0 || (numel & 3) || chunk <= 0 || (chunk & 3) ||
+        chunk * world < numel)
+        return fail(S3G_ERR_ARG, "peer_reduce_gather: staging / sizes (numel, chunk multiples of 4, world * chunk >= numel)");
+    if (!bucket_multicast && !bucket_ptrs) return fail(S3G_ERR_ARG, "peer_reduce_gather: no destination");
+    ReduceGatherArgs a;
+    a.stage = static_cast<float*>(stage_local);
+    a.mc = static_cast<float*>(bucket_multicast);
+    for (int p = 0; p < PEER_MAX_RANKS; ++p) a.bucket[p] = nullptr;
+    if (bucket_ptrs)
+        for (int p = 0; p < world; ++p) {
+            if (!bucket_ptrs[p] || ((uintptr_t)bucket_ptrs[p] & 15)) return fail(S3G_ERR_ARG, "peer_reduce_gather: bucket pointer");
+            a.bucket[p] = static_cast<float*>(const_cast<void*>(bucket_ptrs[p]));
+        }
+    a.world = world; a.rank = rank;
+    a.chunk4 = chunk / 4;
+    a.n4 = numel / 4;
+    const int grid = peer_grid(a.chunk4);
+    switch (world) {
+        case 2: peer_reduce_gather_kernel<2><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        case 4: peer_reduce_gather_kernel<4><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        case 8: peer_reduce_gather_kernel<8><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+        default: peer_reduce_gather_kernel<0><<<grid, PEER_THREADS, 0, stream>>>(a); break;
+    }
+    S3G_CUDA(cudaGetLastError(), "peer_reduce_gather launch");
+    return S3G_OK;
+}
+
 }  // extern "C"

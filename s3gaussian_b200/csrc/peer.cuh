@@ -83,4 +83,50 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_nvls_all_reduce_kernel(floa
     }
 }
 
+// ---- second half of the exchange that preprocess_backward_kernel<.., DP> starts (PeerSink, preprocess.cuh) --------
+// Every rank's visible gradient rows already sit in the staging area of the slice's owner, one sub-slice per source
+// rank: stage = [world][chunk] floats, local.  The owner adds the `world` sub-slices in rank order (every element is
+// summed by exactly one rank in a fixed order -> all ranks end up with identical bits), stores the result into
+// EVERY rank's gradient bucket - one multimem.st through the multicast mapping where the allocation has one (the
+// NVSwitch replicates it), direct peer stores otherwise - and leaves the staging sub-slices zeroed for the next step.
+struct ReduceGatherArgs {
+    float* stage;                       // local staging [world][chunk]
+    float* bucket[PEER_MAX_RANKS];      // peer-mapped gradient buckets (used when mc == nullptr)
+    float* mc;                          // multicast address of the bucket, or nullptr
+    int world, rank;
+    long long chunk4;                   // float4 per slice
+    long long n4;                       // float4 in the whole bucket (the last slice may be shorter)
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(PEER_THREADS) peer_reduce_gather_kernel(const __grid_constant__ ReduceGatherArgs a) {
+    const int world = WORLD > 0 ? WORLD : a.world;
+    const long long lo = (long long)a.rank * a.chunk4;
+    const long long len = (lo + a.chunk4 <= a.n4) ? a.chunk4 : (a.n4 > lo ? a.n4 - lo : 0);
+    float4* st = reinterpret_cast<float4*>(a.stage);
+    for (long long i = (long long)blockIdx.x * PEER_THREADS + threadIdx.x; i < len; i += (long long)gridDim.x * PEER_THREADS) {
+        float4 v[WORLD > 0 ? WORLD : PEER_MAX_RANKS];
+#pragma unroll
+        for (int p = 0; p < (WORLD > 0 ? WORLD : PEER_MAX_RANKS); ++p)
+            if (p < world) v[p] = st[(long long)p * a.chunk4 + i];
+        float4 s = v[0];
+#pragma unroll
+        for (int p = 1; p < (WORLD > 0 ? WORLD : PEER_MAX_RANKS); ++p)
+            if (p < world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < (WORLD > 0 ? WORLD : PEER_MAX_RANKS); ++p)
+            if (p < world) st[(long long)p * a.chunk4 + i] = z;
+        if (a.mc) {
+            float* dst = a.mc + 4 * (lo + i);
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                         ::"l"(dst), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+        } else {
+#pragma unroll
+            for (int p = 0; p < (WORLD > 0 ? WORLD : PEER_MAX_RANKS); ++p)
+                if (p < world) reinterpret_cast<float4*>(a.bucket[p])[lo + i] = s;
+        }
+    }
+}
+
 }  // namespace s3g

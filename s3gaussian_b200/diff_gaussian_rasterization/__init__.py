@@ -240,6 +240,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         proj = _f32c(rs.projmatrix, dev)
         campos = _f32c(rs.campos, dev)
 
+        has_cov_in = cov3Ds_precomp.numel() != 0
+
         def e(name, *shape):
             if _GRAD_SINK is not None:
                 t = _GRAD_SINK(name, shape, dev)
@@ -270,9 +272,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(grad_means3D), _ptr(grad_cov3D), _ptr(grad_sh), _ptr(grad_scales),
                 _ptr(grad_rotations), int(bool(rs.debug)), _stream_ptr(dev))
         bwd = lib.s3g_rasterize_backward
+        peer = getattr(_GRAD_SINK, "peer_sink_struct", None)
         if ctx.has_aux:
             args = args + (grad_out_aux.data_ptr(), grad_aux.data_ptr())
             bwd = lib.s3g_rasterize_backward_aux
+        elif peer is not None:
+            # data-parallel exchange fused into the kernel (dp.FusedGradExchange): the gradient tensors returned
+            # below are views of the exchange's bucket and hold the sums after its finish()
+            if has_cov_in:
+                raise NotImplementedError("FusedGradExchange: precomputed 3-D covariances are not exchanged")
+            import ctypes as _C
+            _GRAD_SINK.note_backward()
+            args = args + (_C.byref(peer),)
+            bwd = lib.s3g_rasterize_backward_dp
         with torch.cuda.device(dev):
             if P > 0:
                 if rs.debug:

@@ -219,3 +219,126 @@ def make_peer_all_reduce(numel: int, device):
         return PeerAllReduce(numel, device), None
     except Exception as e:       # no NVLink peer access, old driver, non-NCCL group, ...
         return None, f"{type(e).__name__}: {e}"
+
+
+class FusedGradExchange:
+    """Per-Gaussian gradient all-reduce with its first half fused into the backward kernel.
+
+    The plain path (PeerAllReduce / ncclAllReduce) lets the backward write its five gradient tensors and then moves
+    the whole 236 B/Gaussian bucket twice over NVLink.  Here the backward's last kernel
+    (preprocess_backward_kernel<.., DP>, s3g_rasterize_backward_dp) stores every VISIBLE Gaussian's gradient values
+    straight into the staging area of the rank that owns that slice of the flat bucket - peer-mapped symmetric
+    memory, plain stores - so the reduce-scatter traffic overlaps the kernel's own HBM work and culled rows never
+    cross the link; `finish()` then runs ONE kernel per rank that sums the `world` staging sub-slices in rank order
+    (bit-identical results on every rank), writes the sums into every rank's bucket (multimem.st through the
+    NVSwitch multicast mapping when the allocation has one, direct peer stores otherwise) and re-zeroes the staging.
+
+        ex = FusedGradExchange({"means3D": (P, 3), "shs": (P, 16, 3), "opacities": (P, 1), ...}, device)
+        ex.install()                    # diff_gaussian_rasterization routes its backward through the sink
+        loss.backward()                 # grads of the named inputs are VIEWS of ex.bucket (not yet summed)
+        ex.finish()                     # barrier | reduce + gather | barrier  -> the views hold the sums
+
+    Layout: one symmetric allocation [bucket | staging]; every tensor starts on a 16-byte boundary of the bucket;
+    slice o of the bucket (chunk floats) is owned by rank o; staging = [world][chunk]."""
+
+    NAMES = ("means3D", "shs", "opacities", "scales", "rotations")
+
+    def __init__(self, shapes: dict, device, group=None):
+        import ctypes as C
+        import warnings
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.offsets, n = {}, 0
+        for k in self.NAMES:
+            if k in shapes and shapes[k] is not None:
+                cnt = 1
+                for v in shapes[k]:
+                    cnt *= int(v)
+                self.offsets[k] = (n, cnt, tuple(int(v) for v in shapes[k]))
+                n = (n + cnt + 3) // 4 * 4
+        for k in ("means3D", "opacities", "scales", "rotations"):
+            if k not in self.offsets:
+                raise ValueError(f"FusedGradExchange needs the shape of {k}")
+        self.numel = n
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        world = dist.get_world_size(self.group)
+        self.chunk = ((n + world - 1) // world + 3) // 4 * 4
+        self.stage_off = (n + 3) // 4 * 4
+        total = self.stage_off + world * self.chunk
+        self.buffer = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.buffer.zero_()
+        self.bucket = self.buffer[:n]
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._bucket_ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        sink = _lib.PeerSink()
+        sink.world, sink.rank, sink.chunk = self.world, self.rank, self.chunk
+        for p in range(self.world):
+            sink.stage[p] = ptrs[p] + 4 * self.stage_off
+        sink.off_means3D = self.offsets["means3D"][0]
+        sink.off_shs = self.offsets["shs"][0] if "shs" in self.offsets else -1
+        sink.off_opacities = self.offsets["opacities"][0]
+        sink.off_scales = self.offsets["scales"][0]
+        sink.off_rotations = self.offsets["rotations"][0]
+        self.peer_sink_struct = sink            # read by diff_gaussian_rasterization's backward
+        self._prev = None
+        self._pending = False
+        torch.cuda.synchronize(device)
+        self.handle.barrier(channel=0)          # every rank's buffer is zeroed before anyone stores into it
+
+    # gradient sink protocol of diff_gaussian_rasterization (name, shape, device) -> tensor or None
+    def __call__(self, name, shape, device):
+        if name not in self.offsets:
+            return None
+        o, cnt, shp = self.offsets[name]
+        if tuple(shape) != shp:
+            raise RuntimeError(f"FusedGradExchange: {name} has shape {tuple(shape)}, the bucket was laid out for {shp}")
+        return self.bucket[o:o + cnt].view(shape)
+
+    def note_backward(self):
+        """called by the rasterizer's backward: the kernel STORES (not adds) this rank's rows into the owners'
+        staging, so exactly one backward may run between two finish() calls"""
+        if self._pending:
+            raise RuntimeError("FusedGradExchange: a second backward before finish() would overwrite the first one's "
+                               "rows in the staging areas (one view per rank and exchange)")
+        self._pending = True
+
+    def install(self):
+        from . import diff_gaussian_rasterization as dgr
+        self._prev = dgr.set_grad_sink(self)
+        return self
+
+    def uninstall(self):
+        from . import diff_gaussian_rasterization as dgr
+        dgr.set_grad_sink(self._prev)
+
+    def finish(self) -> torch.Tensor:
+        """All ranks call this after their backward: returns the bucket holding the summed gradients."""
+        import ctypes as C
+        lib = self._lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.handle.barrier(channel=0)          # every rank's stores have landed
+        stage_local = self.buffer.data_ptr() + 4 * self.stage_off
+        self._lib.check(lib.s3g_peer_reduce_gather(self.world, self.rank, C.c_void_p(stage_local), self._bucket_ptrs,
+                                                   C.c_void_p(self.mc) if self.mc else None, self.numel, self.chunk,
+                                                   stream), "s3g_peer_reduce_gather")
+        self.handle.barrier(channel=1)          # sums visible everywhere, staging zeroed everywhere
+        self._pending = False
+        return self.bucket
+
+
+def make_fused_grad_exchange(shapes: dict, device):
+    """FusedGradExchange, or (None, reason) where symmetric memory cannot be set up."""
+    try:
+        return FusedGradExchange(shapes, device), None
+    except Exception as ex:      # pragma: no cover - depends on the system
+        return None, f"{type(ex).__name__}: {ex}"

@@ -114,6 +114,31 @@ def _worker(rank, world, port, results):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     out["identical_on_all_ranks"] = bool(lo.item() == hi.item())
+    # ---- the same step with the exchange fused into the backward kernel (dp.FusedGradExchange) ---------------
+    ex, why = dp.make_fused_grad_exchange(shapes, dev)
+    out["fused_available"], out["fused_why"] = ex is not None, why
+    if ex is not None:
+        for rep in range(2):                       # twice: the staging must come back zeroed
+            mine2 = grads_of(cams[rank], ex, seed=rank)
+            summed = ex.finish()
+            torch.cuda.synchronize()
+        worst = 0.0
+        for k, (o, c, shp) in ex.offsets.items():
+            want = (a["grads"][k].double() + b["grads"][k].double()).reshape(-1)
+            got = summed[o:o + c].double()
+            worst = max(worst, float((got - want).abs().max() / (want.abs().max() + 1e-30)))
+        out["fused_vs_sequential_relerr"] = worst
+        out["fused_views_alias_bucket"] = bool(mine2["grads"]["shs"].data_ptr() == summed[ex.offsets["shs"][0]:].data_ptr())
+        chk = summed.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["fused_identical_on_all_ranks"] = bool(lo.item() == hi.item())
+        out["fused_multicast"] = bool(ex.mc)
+        # the local (not exchanged) outputs still arrive: screen-space gradient of this rank's view
+        out["fused_means2D_ok"] = bool(torch.equal(mine2["grads"]["means2D"], (a if rank == 0 else b)["grads"]["means2D"]) or
+                                       float((mine2["grads"]["means2D"] - (a if rank == 0 else b)["grads"]["means2D"]).abs().max()) <
+                                       1e-5 * float((a if rank == 0 else b)["grads"]["means2D"].abs().max()))
     # ---- densify on rank 0, broadcast, per-step statistics ---------------------------------------------------
     from s3gaussian_b200.gaussian_model import GaussianModel, default_optimization_params, PARAM_GROUPS, _ATTR
     T = lambda t: t.to(dev)
@@ -158,6 +183,9 @@ def test_two_rank_collectives_sink_and_broadcast(built_lib):
         assert r["peer_equals_nccl"]
         assert r["nvls_equals_nccl"] in (True, None), r.get("nvls_maxerr")
         assert r["dp_vs_sequential_relerr"] < 1e-5
+        assert r["fused_available"], r["fused_why"]
+        assert r["fused_vs_sequential_relerr"] < 1e-5, r["fused_vs_sequential_relerr"]
+        assert r["fused_identical_on_all_ranks"] and r["fused_views_alias_bucket"] and r["fused_means2D_ok"]
         assert r["identical_on_all_ranks"] and r["bc_identical"]
         assert r["bc_points"] > 20_000
     assert r0["stats_sum"] == r1["stats_sum"]

@@ -114,13 +114,22 @@ class Deformation(nn.Module):
         super().__init__()
         if D != 1 or W != 64:
             raise NotImplementedError("the fused decoder is built for defor_depth=1, net_width=64")
-        for bad in ("no_grid", "empty_voxel", "static_mlp", "apply_rotation"):
-            if getattr(args, bad, False):
-                raise NotImplementedError(f"{bad}=True is outside the fused hot path (SURVEY.md 5: default False)")
-        if getattr(args, "grid_pe", 0) not in (0, 1):
-            raise NotImplementedError("grid_pe > 1 is outside the fused hot path")
+        if getattr(args, "no_grid", False):
+            raise NotImplementedError("no_grid=True: the reference itself cannot run it (query_time leaves `hidden` "
+                                      "undefined, scene/deformation.py:80-91)")
+        if getattr(args, "grid_pe", 0) != 0:
+            raise NotImplementedError("grid_pe != 0: the reference sizes feature_out for 3x the features but feeds it "
+                                      "1x or (1+2*grid_pe)x (scene/deformation.py:47-50,86-87); not runnable upstream")
         self.D, self.W, self.args = D, W, args
+        # switches that stay in PyTorch: deformation_cold.py
+        self.cold = bool(getattr(args, "empty_voxel", False) or getattr(args, "static_mlp", False) or
+                         getattr(args, "apply_rotation", False))
         self.grid = HexPlaneField(args.bounds, args.kplanes_config, args.multires)
+        if getattr(args, "empty_voxel", False):
+            from .deformation_cold import DenseGrid
+            self.empty_voxel = DenseGrid(channels=1, world_size=[64, 64, 64])
+        if getattr(args, "static_mlp", False):
+            self.static_mlp = nn.Sequential(nn.ReLU(), nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 1))
         self.feature_out = nn.Sequential(nn.Linear(self.grid.feat_dim, W))
 
         def head(k):
@@ -136,6 +145,8 @@ class Deformation(nn.Module):
 
     def set_aabb(self, xyz_max, xyz_min):
         self.grid.set_aabb(xyz_max, xyz_min)
+        if getattr(self.args, "empty_voxel", False):
+            self.empty_voxel.set_aabb(xyz_max, xyz_min)
 
     def get_mlp_parameters(self):
         return [p for n, p in self.named_parameters() if "grid" not in n]
@@ -182,6 +193,11 @@ class deform_network(nn.Module):
         """(means3D, scales, rotations, opacity, shs, dx, feat, dshs) - raw (pre-activation)
         scales / rotations / opacity, like scene/deformation.py:216-231."""
         t = float(times_sel.reshape(-1)[0]) if torch.is_tensor(times_sel) else float(times_sel)
+        if self.deformation_net.cold:
+            from . import deformation_cold
+            if not point.is_cuda:
+                raise RuntimeError("s3gaussian_b200 has no CPU path: point must be a CUDA tensor")
+            return deformation_cold.forward_dynamic(self.deformation_net, point, scales, rotations, opacity, shs, t)
         zero3 = torch.zeros(3, device=point.device)
         out = _DeformFront.apply(self, t, zero3, 0, True, point, scales, rotations, opacity, shs,
                                  *self._param_list())
@@ -195,6 +211,12 @@ class deform_network(nn.Module):
     def render_front(self, xyz, scaling, rotation, opacity, shs, time, campos, active_sh_degree):
         """One kernel: deformation + activations + SH->RGB (gaussian_renderer/__init__.py:89-117).
         Returns (means3D_final, scales_act, rot_act, opacity_act, colors_precomp, dx, dshs, feat)."""
+        if self.deformation_net.cold:
+            from . import deformation_cold
+            if not xyz.is_cuda:
+                raise RuntimeError("s3gaussian_b200 has no CPU path: xyz must be a CUDA tensor")
+            return deformation_cold.render_front(self.deformation_net, xyz, scaling, rotation, opacity, shs, float(time),
+                                                 campos, active_sh_degree)
         return _DeformFront.apply(self, float(time), campos, int(active_sh_degree), False, xyz, scaling, rotation,
                                   opacity, shs, *self._param_list())
 

@@ -67,8 +67,27 @@ def run():
     before = m._features_rest.data[keep].clone()
     m.prune_points(~keep)
     assert torch.equal(m._features_rest.data, before)
+    # spatial sort (row gather + our radix sort): a permutation of every per-Gaussian tensor
+    xyz_before = m._xyz.data.clone()
+    order = m.spatial_sort()
+    assert torch.equal(m._xyz.data, xyz_before[order]) and torch.equal(torch.sort(order).values, torch.arange(order.numel(), device=dev))
+    # colour + feature image on one binning (s3g_rasterize_forward_aux / _backward_aux) == two passes
+    import util
+    from s3gaussian_b200 import synthetic as syn, diff_gaussian_rasterization as dgr
+    cloud, cam = syn.make_small_scene(P=500, width=96, height=64, seed=6)
+    dd = util.scene_inputs(cloud, cam, mode="rgb")
+    rast = dgr.GaussianRasterizer(util.settings_for(dgr, dd, dev))
+    tt = {k: dd[k].to(dev).requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp")}
+    feat = torch.rand(500, 3, device=dev).requires_grad_(True)
+    m2d = torch.zeros(500, 3, device=dev, requires_grad=True)
+    kw = dict(means3D=tt["means3D"], means2D=m2d, opacities=tt["opacities"], scales=tt["scales"], rotations=tt["rotations"])
+    c1, r1, d1, a1 = rast.forward_aux(colors_aux=feat, colors_precomp=tt["colors_precomp"], **kw)
+    (c1.sum() + a1.sum() * 0.5 + d1.sum() * 0.1).backward()
+    g_fused = feat.grad.clone()
+    a2, _, _ = rast(colors_precomp=feat.detach(), **kw)
+    assert rel(a1.detach().cpu(), a2.detach().cpu()) < 1e-6 and float(g_fused.abs().max()) > 0
     # 3-NN scale initialiser
     from s3gaussian_b200.simple_knn import distCUDA2
     pts = torch.rand(700, 3, generator=torch.Generator().manual_seed(5)) * 10
     assert np.allclose(distCUDA2(pts.to(dev)).cpu().numpy(), knn_oracle.mean_dist2(pts.numpy()), rtol=2e-6)
-    print("smoke extra ok: deform fwd/bwd (tcgen05 forward), image loss, plane regularisers, Adam, stats, row gather, 3-NN")
+    print("smoke extra ok: deform fwd/bwd (tcgen05 forward), image loss, plane regularisers, Adam, stats, row gather, spatial sort, shared-binning aux pass, 3-NN")

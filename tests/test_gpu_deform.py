@@ -256,3 +256,37 @@ def test_umma_selftest(K, N, built_lib):
         torch.cuda.synchronize()
         assert rc == 0
         assert float((D.double() - ref).abs().max() / ref.abs().max()) < tol
+
+
+def test_cold_switches_render_through_the_pytorch_path(built_lib):
+    """static_mlp / apply_rotation ("keep in PyTorch"): render(stage='fine') runs through
+    deformation_cold.py + our rasterizer and equals the reference module's outputs fed to the same rasterizer."""
+    if not ref_ext.deform_available():
+        pytest.skip("oracle/_ref not present")
+    from s3gaussian_b200 import synthetic as syn
+    from s3gaussian_b200.deformation import deform_network
+    from s3gaussian_b200.gaussian_renderer import render, PipelineParams, GaussianModelLite
+    ref_dn, _ = ref_ext.load_ref_deform()
+    flags = dict(static_mlp=True, apply_rotation=True, no_ds=False, no_dr=False, no_do=False)
+    reso, mres = (16, 12, 10, 7), (1, 2, 4)
+    cloud, cam = syn.make_small_scene(P=300, width=80, height=48, seed=3)
+    cam.time = 0.3
+    st = syn.make_deform_state(5, reso, mres, aabb=((9.0, 4.0, 3.0), (-2.0, -4.0, -3.0)), weight_scale=0.2)
+    theirs = ref_dn(ref_ext.ref_deform_args(reso, mres, **flags))
+    theirs.deformation_net.set_aabb([9.0, 4.0, 3.0], [-2.0, -4.0, -3.0])
+    theirs.load_state_dict(st, strict=False)
+    mine = deform_network(ref_ext.ref_deform_args(reso, mres, **flags))
+    mine.deformation_net.set_aabb([9.0, 4.0, 3.0], [-2.0, -4.0, -3.0])
+    assert not any(mine.load_state_dict(theirs.state_dict(), strict=False))
+    pc = GaussianModelLite(cloud, mine).to(DEV)
+    theirs = theirs.to(DEV)
+    bg = torch.zeros(3, device=DEV)
+    out = render(cam.to(DEV), pc, PipelineParams(), bg, stage="fine", return_dx=True, render_feat=True)
+    (out["render"].sum() + out["feat"].sum() + out["depth"].sum()).backward()
+    assert pc._xyz.grad is not None and float(pc._xyz.grad.abs().max()) > 0
+    xyz, shs = cloud.xyz.to(DEV), cloud.get_features().to(DEV)
+    t = torch.full((300, 1), cam.time, device=DEV)
+    m3, s2, r2, o2, shf, dx, feat, dshs = theirs(xyz, cloud.scaling.to(DEV), cloud.rotation.to(DEV), cloud.opacity.to(DEV), shs, t)
+    assert rel(out["dx"].detach().cpu().numpy(), dx.detach().cpu().numpy()) < 1e-5
+    assert rel(out["dshs"].detach().cpu().numpy(), dshs.detach().cpu().numpy()) < 1e-5
+    assert out["render"].shape == (3, 48, 80) and torch.isfinite(out["render"]).all() and float(out["render"].max()) > 0

@@ -44,10 +44,15 @@ def test_planes_are_channels_last_and_survive_load_state_dict():
 
 
 def test_unsupported_configs_and_cpu_inputs_fail_loudly():
+    # switches that run through the PyTorch cold path (deformation_cold.py) construct; they refuse CPU tensors too
+    for flag in ("empty_voxel", "static_mlp"):
+        cold = make(**{flag: True})
+        assert cold.deformation_net.cold
+        z = torch.zeros(4, 3)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            cold(z, z, torch.zeros(4, 4), torch.zeros(4, 1), torch.zeros(4, 16, 3), torch.zeros(4, 1))
     with pytest.raises(NotImplementedError):
-        make(empty_voxel=True)
-    with pytest.raises(NotImplementedError):
-        make(static_mlp=True)
+        make(no_grid=True)
     with pytest.raises(NotImplementedError):
         deform_network(ref_ext.ref_deform_args((8, 8, 8, 5), (1,), net_width=128))
     net = make()

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--height", type=int, default=640)
     ap.add_argument("--fine", action="store_true", help="train the HexPlane deformation stage too")
+    ap.add_argument("--checkpoint", default="", help="write and re-load a reference-format checkpoint here (needs --fine)")
     a = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: s3gaussian_b200 has no CPU path")
@@ -82,6 +83,7 @@ def main():
             if it > 50 and it % 100 == 0:
                 gaussians.densify(0.0002, 0.005, extent, 20 if it > 3000 else None)
                 gaussians.prune(0.0002, 0.005, extent, 20 if it > 3000 else None)
+                gaussians.spatial_sort()      # ours: keep the model in Morton order (densify appends at the end)
         gaussians.optimizer.step()                                               # one launch over all groups
         gaussians.optimizer.zero_grad(set_to_none=True)
         if it % 50 == 0:
@@ -89,6 +91,16 @@ def main():
                   f"points {gaussians.get_xyz.shape[0]}")
     e1.record()
     torch.cuda.synchronize()
+    # checkpoint in the reference's format (train.py:531: torch.save((gaussians.capture(), iteration), path)) and back
+    if a.checkpoint and not a.fine:
+        print("--checkpoint needs --fine: capture() stores the deformation network's state_dict")
+    elif a.checkpoint:
+        torch.save((gaussians.capture(), a.iters), a.checkpoint)
+        model_args, first_iter = torch.load(a.checkpoint, weights_only=False)
+        resumed = GaussianModel(3, deformation=gaussians._deformation)
+        resumed.restore(model_args, opt)
+        assert torch.equal(resumed.get_xyz, gaussians.get_xyz) and first_iter == a.iters
+        print(f"checkpoint {a.checkpoint}: {resumed.get_xyz.shape[0]} points restored (iteration {first_iter})")
     if a.iters > 10:
         print(f"{e0.elapsed_time(e1) / (a.iters - 10):.3f} ms per iteration over the last {a.iters - 10}")
 

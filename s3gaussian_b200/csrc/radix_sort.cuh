@@ -313,6 +313,7 @@ scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_bid;
     __shared__ uint64_t s_prefix;
+    __shared__ uint64_t s_part[SCAN_THREADS / 32];
     const int tid = threadIdx.x;
     if (tid == 0) s_bid = atomicAdd(&misc[0], 1u);
     __syncthreads();
@@ -330,45 +331,36 @@ scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict
     }
     uint32_t block_total;
     uint32_t texcl = block_excl_scan_256(sum, s_warp, &block_total);
-    if (tid < 32) {
-        // decoupled look-back, one warp wide: lane l inspects predecessor bid-1-l, so a chain of aggregates
-        // resolves in one L2 round trip per 32 blocks instead of one per block
-        const uint32_t F = 0xffffffffu;
-        const uint64_t VAL = (1ull << 62) - 1;
-        const int lane = tid;
-        uint64_t excl = 0;
-        if (bid == 0) {
-            if (lane == 0) st_volatile_u64(&status[0], (2ull << 62) | (uint64_t)block_total);
-        } else {
-            if (lane == 0) st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
-            int p = (int)bid - 1;
-            while (true) {
-                const int idx = p - lane;
-                const uint64_t s = idx >= 0 ? ld_volatile_u64(&status[idx]) : (2ull << 62);   // "block -1": inclusive 0
-                const uint32_t f = (uint32_t)(s >> 62);
-                const unsigned notready = __ballot_sync(F, f == 0);
-                const unsigned incl = __ballot_sync(F, f == 2);
-                const int first = incl ? __ffs(incl) - 1 : 32;
-                const unsigned need = first < 32 ? ((2u << first) - 1u) : F;   // lanes 0..first
-                if (notready & need) continue;                                  // not all published yet: look again
-                uint64_t part = (lane <= first) ? (s & VAL) : 0ull;
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(F, part, o);
-                excl += part;
-                if (first < 32) break;
-                p -= 32;
-            }
-            if (lane == 0) st_volatile_u64(&status[bid], (2ull << 62) | (excl + block_total));
+    // Prefix over the preceding blocks.  The grid is (nearly) one wave, so every block publishes its aggregate at
+    // about the same time and a classic decoupled look-back degenerates into a chain (block k needs k/32 round trips
+    // to meet an inclusive prefix: 30 us for 977 blocks).  Instead every thread fetches one predecessor's AGGREGATE
+    // per window of 256 blocks (independent spin on its own word), the block adds them up: ceil(bid/256) round
+    // trips.  Predecessors hold lower tickets, i.e. they have started and publish without waiting on anyone later.
+    if (tid == 0) st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
+    uint64_t part = 0;      // 64-bit: the caller rejects counts >= 2^30, but only after it has seen the true total
+    for (int base = (int)bid - 1; base >= 0; base -= SCAN_THREADS) {
+        const int idx = base - tid;
+        if (idx >= 0) {
+            uint64_t sv;
+            do { sv = ld_volatile_u64(&status[idx]); } while ((sv >> 62) == 0);
+            part += sv & ((1ull << 62) - 1);
         }
-        if (lane == 0) {
-            s_prefix = excl;
-            if (bid == nblk - 1) {
-                *reinterpret_cast<uint64_t*>(misc + 2) = excl + block_total;
-                if (host_total) {       // the host learns the count without a copy or a stream synchronisation
-                    host_total[0] = excl + block_total;
-                    __threadfence_system();
-                    host_total[1] = seq;
-                }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t excl = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) excl += s_part[w];
+        s_prefix = excl;
+        if (bid == nblk - 1) {
+            *reinterpret_cast<uint64_t*>(misc + 2) = excl + block_total;
+            if (host_total) {       // the host learns the count without a copy or a stream synchronisation
+                host_total[0] = excl + block_total;
+                __threadfence_system();
+                host_total[1] = seq;
             }
         }
     }

@@ -259,7 +259,7 @@ def test_umma_selftest(K, N, built_lib):
 
 
 def test_cold_switches_render_through_the_pytorch_path(built_lib):
-    """static_mlp / apply_rotation ("keep in PyTorch"): render(stage='fine') runs through
+    """apply_rotation ("keep in PyTorch"): render(stage='fine') runs through
     deformation_cold.py + our rasterizer and equals the reference module's outputs fed to the same rasterizer."""
     if not ref_ext.deform_available():
         pytest.skip("oracle/_ref not present")
@@ -267,7 +267,9 @@ def test_cold_switches_render_through_the_pytorch_path(built_lib):
     from s3gaussian_b200.deformation import deform_network
     from s3gaussian_b200.gaussian_renderer import render, PipelineParams, GaussianModelLite
     ref_dn, _ = ref_ext.load_ref_deform()
-    flags = dict(static_mlp=True, apply_rotation=True, no_ds=False, no_dr=False, no_do=False)
+    # (static_mlp / empty_voxel with random weights scatter the means off screen; their arithmetic is covered bit for
+    # bit on the CPU by tests/test_deform_cold_host.py - here the quaternion-product switch keeps a renderable scene)
+    flags = dict(apply_rotation=True, no_ds=False, no_dr=False, no_do=False)
     reso, mres = (16, 12, 10, 7), (1, 2, 4)
     cloud, cam = syn.make_small_scene(P=300, width=80, height=48, seed=3)
     cam.time = 0.3

@@ -1,4 +1,5 @@
 // api_deform_bwd.cu - extern "C" entry points of the fused HexPlane + decoder stage, backward (see include/s3g_b200.h).
+#include <cstdlib>
 #include "deform_host.cuh"
 
 using namespace s3g;
@@ -118,7 +119,10 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int blocks = std::min((P + 7) / 8, sms * 8);
-        if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
+        // A/B switch while tuning (profiles/r02h): 3 resident blocks per SM (80 registers, 27 spilled words) vs 2
+        static const int minb = [] { const char* e = std::getenv("S3G_SCATTER_MINB"); return e ? std::atoi(e) : 2; }();
+        if (d.L == 4 && minb == 3) hexplane_scatter_kernel<4, 3><<<blocks, 256, 0, stream>>>(sc);
+        else if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
         else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
         S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
     }

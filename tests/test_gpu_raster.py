@@ -287,12 +287,14 @@ def test_extreme_opacity_and_anisotropy(ours, oracle_lib):
         assert e < 2e-2, (k, e)
     if ref_ext.available():
         ref = ref_ext.load()
-        r1 = util.run_module(ref, d, DEV, gc, gd)
-        r2 = util.run_module(ref, d, DEV, gc, gd)
+        # the reference's spread is itself a random sample (two runs can happen to agree to 3e-4 or differ by 3e-3),
+        # so it is taken as the largest of four runs against the first, with a floor of 1e-2 = 5 x its typical value
+        runs = [util.run_module(ref, d, DEV, gc, gd) for _ in range(5)]
         for k in names:
-            noise = util.relerr(r1["grads"][k].cpu().numpy(), r2["grads"][k].cpu().numpy())
-            e = util.relerr(out["grads"][k].cpu().numpy(), r1["grads"][k].cpu().numpy())
-            assert e < max(5 * noise, TOL), (k, e, noise)
+            r0 = runs[0]["grads"][k].cpu().numpy()
+            noise = max(util.relerr(r["grads"][k].cpu().numpy(), r0) for r in runs[1:])
+            e = util.relerr(out["grads"][k].cpu().numpy(), r0)
+            assert e < max(5 * noise, 1e-2), (k, e, noise)
 
 
 # ------------------------------------------- size-independent properties, full size

@@ -119,10 +119,7 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int blocks = std::min((P + 7) / 8, sms * 8);
-        // A/B switch while tuning (profiles/r02h): 3 resident blocks per SM (80 registers, 27 spilled words) vs 2
-        static const int minb = [] { const char* e = std::getenv("S3G_SCATTER_MINB"); return e ? std::atoi(e) : 2; }();
-        if (d.L == 4 && minb == 3) hexplane_scatter_kernel<4, 3><<<blocks, 256, 0, stream>>>(sc);
-        else if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
+        if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
         else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
         S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
     }

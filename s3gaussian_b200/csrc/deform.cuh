@@ -994,8 +994,10 @@ struct ScatterArgs {
     float* gplanes[S3G_MAX_LEVELS][6];
     float* d_xyz;                          // [P,3], += grid path
 };
-template <int LT, int MINB = 2>   // MINB: resident blocks per SM the register budget is capped for
-__global__ void __launch_bounds__(256, MINB) hexplane_scatter_kernel(ScatterArgs a) {
+// (capping the registers at 80 for a third resident block per SM was measured: 26.5 vs 25.7 ms for the whole deform
+// fwd+bwd at 2 M - the kernel is bound by L2 atomic / load throughput, not by occupancy; profiles/r02h_scatter_ab.log)
+template <int LT>
+__global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a) {
     const DNet& n = a.net;
     const int L = LT > 0 ? LT : n.L;
     const int lane = threadIdx.x & 31;

@@ -427,3 +427,19 @@ def test_shared_binning_two_colour_sets_equal_two_passes(ours):
         for k in g3:
             e = util.relerr(g1[k].cpu().numpy(), g3[k].cpu().numpy())
             assert e < TOL, (k, e)
+
+
+def test_more_than_16k_tiles_uses_the_global_histogram_path(ours, oracle_lib):
+    """2576x1664 = 161 x 104 = 16 744 tiles: the tile histogram no longer fits the emit kernel's shared-memory table
+    (emit_instances_kernel<false>, direct global atomics) and the tile ids need 15 key bits."""
+    from s3gaussian_b200 import synthetic as syn
+    cloud, cam = syn.make_small_scene(P=2500, width=2576, height=1664, seed=41)
+    d = util.scene_inputs(cloud, cam, mode="rgb")
+    o = util.oracle_run(oracle_lib, d)
+    color, radii, depth, R, views = util.ours_forward_state(d, DEV)
+    assert views["ranges"].shape[0] == 161 * 104
+    check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
+                                         tiles_touched=o["geometry"]["tiles_touched"],
+                                         point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                                         ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    assert util.relerr(color.cpu().numpy(), o["color"]) < TOL

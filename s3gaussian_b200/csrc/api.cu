@@ -66,6 +66,7 @@ struct HostCount {
     volatile uint64_t* dev = nullptr;
     uint64_t seq = 0;
     int64_t last_capacity = 0;
+    int scan_resident_blocks = 0;
 };
 HostCount* host_count() {
     static thread_local HostCount table[64];
@@ -343,9 +344,20 @@ int64_t forward_impl(s3g_alloc_fn geom_alloc, void* geom_user, s3g_alloc_fn binn
     const uint64_t seq = ++hc->seq;
     {
         const uint32_t nblk = (uint32_t)div_up64(P, SCAN_TILE);
+        if (hc->scan_resident_blocks == 0) {        // once per (thread, device): how many scan blocks fit at the same time
+            int per_sm = 0, sms = 0, dev = 0;
+            S3G_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+            S3G_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
+            S3G_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_tiles_kernel, SCAN_THREADS, 0), "occupancy");
+            hc->scan_resident_blocks = std::max(1, per_sm * sms);
+        }
+        // (a concurrent kernel on another stream can only delay residency: its slots free up when it ends, and a
+        //  grid that fits is never waiting on a block that cannot eventually be placed)
+        const int use_tickets = (int64_t)nblk > hc->scan_resident_blocks ? 1 : 0;
         scan_tiles_kernel<<<nblk, SCAN_THREADS, 0, stream>>>(geom.order_a, geom.tiles_touched,
                                                              (uint32_t)P, geom.offsets,
-                                                             geom.scan_status, geom.scan_misc, hc->dev, seq);
+                                                             geom.scan_status, geom.scan_misc, hc->dev, seq,
+                                                             use_tickets);
         S3G_STAGE("scan");
     }
     const uint32_t* n_dev = geom.scan_misc + 2;     // low word of the u64 total (checked < 2^30 below)

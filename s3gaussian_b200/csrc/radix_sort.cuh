@@ -309,15 +309,21 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
                   uint32_t n, uint32_t* __restrict__ offsets, uint64_t* status, uint32_t* misc,
-                  volatile uint64_t* host_total /*[2] mapped pinned: {total, sequence}*/, uint64_t seq) {
+                  volatile uint64_t* host_total /*[2] mapped pinned: {total, sequence}*/, uint64_t seq,
+                  int use_tickets) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_bid;
     __shared__ uint64_t s_prefix;
     __shared__ uint64_t s_part[SCAN_THREADS / 32];
     const int tid = threadIdx.x;
-    if (tid == 0) s_bid = atomicAdd(&misc[0], 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
+    // Block order: a ticket (start order) when the grid is larger than what can be resident at once - a block may
+    // only wait on blocks that have started; blockIdx when every block is resident anyway (the host checks): ~1000
+    // same-address ticket atomics serialise in L2 for 10-20 us, more than the rest of the kernel.
+    if (use_tickets) {
+        if (tid == 0) s_bid = atomicAdd(&misc[0], 1u);
+        __syncthreads();
+    }
+    const uint32_t bid = use_tickets ? s_bid : blockIdx.x;
     const uint32_t nblk = gridDim.x;
     // blocked arrangement: thread owns SCAN_ITEMS consecutive items
     const uint32_t base = bid * SCAN_TILE + tid * SCAN_ITEMS;

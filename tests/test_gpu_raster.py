@@ -438,8 +438,26 @@ def test_more_than_16k_tiles_uses_the_global_histogram_path(ours, oracle_lib):
     o = util.oracle_run(oracle_lib, d)
     color, radii, depth, R, views = util.ours_forward_state(d, DEV)
     assert views["ranges"].shape[0] == 161 * 104
-    check_state_vs(views, radii, R, dict(num_rendered=o["R"], radii=o["radii"],
-                                         tiles_touched=o["geometry"]["tiles_touched"],
-                                         point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
-                                         ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    # 4.3 M pixels x ~450 list entries: the CPU oracle's expf (glibc) and CUDA's differ in the last bit often enough
+    # for a handful of alpha >= 1/255 decisions to flip, so n_contrib is compared bit for bit against the REFERENCE
+    # EXTENSION (same device arithmetic) and only approximately against the oracle
+    nc = views["n_contrib"].copy()
+    check_state_vs(dict(views, n_contrib=o["image"]["n_contrib"]), radii, R,
+                   dict(num_rendered=o["R"], radii=o["radii"], tiles_touched=o["geometry"]["tiles_touched"],
+                        point_list=o["binning"]["point_list"], keys=o["binning"]["keys"],
+                        ranges=o["binning"]["ranges"], n_contrib=o["image"]["n_contrib"]))
+    assert int((nc != o["image"]["n_contrib"]).sum()) <= 8
     assert util.relerr(color.cpu().numpy(), o["color"]) < TOL
+    if ref_ext.available():
+        ref = ref_ext.load()
+        E = torch.Tensor([])
+        g = lambda k: d[k].to(DEV).contiguous() if d[k] is not None else E
+        R0, rc, rdep, rrad, gb, bb, ib = ref._C.rasterize_gaussians(
+            d["bg"].to(DEV), g("means3D"), g("colors_precomp"), g("opacities"), g("scales"), g("rotations"), 1.0,
+            g("cov3D_precomp"), d["viewmatrix"].to(DEV), d["projmatrix"].to(DEV), d["tanfovx"], d["tanfovy"], d["H"], d["W"],
+            g("shs"), d["sh_degree"], d["campos"].to(DEV), False, False)
+        torch.cuda.synchronize()
+        ri = ref_ext.decode_image(ib, d["W"] * d["H"])
+        assert R0 == R
+        np.testing.assert_array_equal(nc, ri["n_contrib"])
+        assert util.relerr(color.cpu().numpy(), rc.cpu().numpy()) < TOL

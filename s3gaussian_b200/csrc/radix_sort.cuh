@@ -112,6 +112,12 @@ sort_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, int begin_b
 
 // ---- one digit pass --------------------------------------------------------
 // grid: exactly ceil(n / SORT_TILE) blocks.  status: [nblk][RADIX] zeroed.
+// Block order = data order must be START order (a block only waits on blocks that are running), so positions are
+// handed out by a ticket atomic.  Measured alternatives (profiles/r02k_sort_modes.log, six passes per step):
+// blockIdx order (no ticket; relies on in-order dispatch, not used) is 35 us per step faster - ~450 same-address
+// atomics at the start of every pass serialise in L2; one ticket per thread-block CLUSTER of 8 (co-scheduled blocks,
+// ticket shared through distributed shared memory) is 46 us SLOWER - gang-scheduling eight 43 KB blocks costs more
+// than the atomics it saves.  Per-block tickets stay.
 template <bool WRITE_KEYS>
 __global__ void __launch_bounds__(SORT_THREADS)   // (capping at 64 registers for a 4th block per SM measured slower)
 sort_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
@@ -284,12 +290,10 @@ cudaError_t radix_sort_pairs(uint32_t n, uint32_t* keys_in, uint32_t* vals_in,
         uint32_t* status = st.status + (size_t)p * nblk * RADIX;
         if (dst_k)
             sort_onesweep_kernel<true><<<nblk, SORT_THREADS, 0, stream>>>(
-                src_k, src_v, dst_k, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status,
-                st.tickets + p);
+                src_k, src_v, dst_k, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status, st.tickets + p);
         else
             sort_onesweep_kernel<false><<<nblk, SORT_THREADS, 0, stream>>>(
-                src_k, src_v, nullptr, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status,
-                st.tickets + p);
+                src_k, src_v, nullptr, dst_v, n, n_dev, shift, mask, st.hist + p * RADIX, status, st.tickets + p);
         src_k = dst_k;
         src_v = dst_v;
     }

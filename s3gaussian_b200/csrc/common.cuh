@@ -85,7 +85,7 @@ struct GeomState {
     uint32_t* order_b;
     uint32_t* offsets;       // exclusive scan of tiles_touched in depth order
     uint64_t* scan_status;   // chained-scan look-back words
-    uint32_t* scan_misc;     // [0]=ticket, [2..3]=total (u64): the instance count, read on the device by the binning
+    uint32_t* scan_misc;     // [0]=ticket, [1]=grid-barrier arrivals, [2..3]=total (u64): the instance count, read on the device by the binning
     SortTemp sort;
     size_t zero_bytes;       // scan_status .. end of sort temp: zeroed by ONE memset before preprocess
     __host__ static GeomState carve(char* base, int64_t P, size_t* total = nullptr) {

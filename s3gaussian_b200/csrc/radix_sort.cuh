@@ -341,19 +341,33 @@ scan_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict
     }
     uint32_t block_total;
     uint32_t texcl = block_excl_scan_256(sum, s_warp, &block_total);
-    // Prefix over the preceding blocks.  The grid is (nearly) one wave, so every block publishes its aggregate at
-    // about the same time and a classic decoupled look-back degenerates into a chain (block k needs k/32 round trips
-    // to meet an inclusive prefix: 30 us for 977 blocks).  Instead every thread fetches one predecessor's AGGREGATE
-    // per window of 256 blocks (independent spin on its own word), the block adds them up: ceil(bid/256) round
-    // trips.  Predecessors hold lower tickets, i.e. they have started and publish without waiting on anyone later.
-    if (tid == 0) st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
+    // Prefix over the preceding blocks.
     uint64_t part = 0;      // 64-bit: the caller rejects counts >= 2^30, but only after it has seen the true total
-    for (int base = (int)bid - 1; base >= 0; base -= SCAN_THREADS) {
-        const int idx = base - tid;
-        if (idx >= 0) {
-            uint64_t sv;
-            do { sv = ld_volatile_u64(&status[idx]); } while ((sv >> 62) == 0);
-            part += sv & ((1ull << 62) - 1);
+    if (!use_tickets) {
+        // The whole grid is resident (host-checked): publish the block sum, meet at a grid-wide barrier (one arrival
+        // counter, ONE polling thread per block), then every thread adds up its share of the preceding sums.  No
+        // thread ever polls a neighbour's status word - 250 k threads spinning on L2 lines (the look-back below at
+        // one wave) delay the very stores they wait for.
+        if (tid == 0) {
+            st_volatile_u64(&status[bid], (uint64_t)block_total);
+            __threadfence();
+            atomicAdd(&misc[1], 1u);
+            while (ld_volatile_u32(&misc[1]) < nblk) {}
+        }
+        __syncthreads();
+        for (int idx = tid; idx < (int)bid; idx += SCAN_THREADS) part += ld_volatile_u64(&status[idx]);
+    } else {
+        // Larger grids: every thread fetches one predecessor's AGGREGATE per window of 256 blocks (independent spin on
+        // its own word), the block adds them up: ceil(bid/256) round trips.  Predecessors hold lower tickets, i.e. they
+        // have started and publish without waiting on anyone later.
+        if (tid == 0) st_volatile_u64(&status[bid], (1ull << 62) | (uint64_t)block_total);
+        for (int base = (int)bid - 1; base >= 0; base -= SCAN_THREADS) {
+            const int idx = base - tid;
+            if (idx >= 0) {
+                uint64_t sv;
+                do { sv = ld_volatile_u64(&status[idx]); } while ((sv >> 62) == 0);
+                part += sv & ((1ull << 62) - 1);
+            }
         }
     }
 #pragma unroll

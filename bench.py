@@ -280,6 +280,25 @@ def main():
 
     copy_stream = torch.cuda.Stream(device=dev)
     copied = torch.cuda.Event()
+    # The step's loss, same definition for both arms: Ll1 + 0.5 * compute_depth("l2") with lambda_dssim = 0
+    # (train.py:395-419; SSIM is not evaluated when its weight is 0).  Each arm computes it with ITS OWN loss code:
+    # ours through s3gaussian_b200.losses (fused kernels, no SSIM stencil), the reference arm through the reference's
+    # utils/loss_utils.py functions (torch ops) - plain torch means only where oracle/_ref has no loss_utils.
+    if a.impl == "ours":
+        from s3gaussian_b200 import losses as _losses
+
+        def e2e_loss(color, img_d, depth, dep_d):
+            return _losses.training_loss(color, img_d, depth, dep_d, lambda_dssim=0.0, lambda_depth=0.5)
+        e2e_loss_what = "s3gaussian_b200.losses.training_loss(lambda_dssim=0): fused L1 + depth-L2 kernels"
+    else:
+        _lu = ref_ext_mod.load_ref_loss_utils() if ref_ext_mod.loss_utils_available() else None
+
+        def e2e_loss(color, img_d, depth, dep_d):
+            if _lu is None:
+                return (color - img_d).abs().mean() + 0.5 * ((depth - dep_d) ** 2).mean()
+            return _lu.l1_loss(color, img_d) + 0.5 * _lu.compute_depth("l2", depth, dep_d)
+        e2e_loss_what = "reference utils/loss_utils.py l1_loss + 0.5 * compute_depth('l2')" if _lu is not None else \
+            "plain torch L1 + 0.5 * L2 (loss_utils.py not in oracle/_ref)"
 
     def step_e2e():
         zero_grads()
@@ -300,7 +319,7 @@ def main():
         main.wait_event(copied)
         img_d.record_stream(main)
         dep_d.record_stream(main)
-        loss = (color - img_d).abs().mean() + 0.5 * ((depth - dep_d) ** 2).mean()
+        loss = e2e_loss(color, img_d, depth, dep_d)
         loss.backward()
         allreduce_grads()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -535,8 +554,9 @@ def main():
                    "l2": "inputs (>= 470 MB of Gaussian parameters + sort arenas) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": round(world * P / (e2e_ms * 1e-3), 1), "unit": "Gaussians/s", "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
-                "what": "camera + GT image/depth H2D from pinned memory, render through the GaussianRasterizer API, "
-                        "L1+depth-L2 loss, backward, loss D2H"},
+                "what": "camera + GT image/depth H2D from pinned memory (images on a copy stream under the forward), render "
+                        "through the GaussianRasterizer API, loss = Ll1 + 0.5 * depth-L2 (train.py:395-411, lambda_dssim = 0) "
+                        "by " + e2e_loss_what + ", backward, loss D2H"},
         # kernels of libs3g_b200.so per step x steps, counted by CUPTI in an untimed pass (all kernels incl. torch
         # glue in gpu_launches_all)
         "gpu_launches": (launches_ours * a.steps if launches_ours is not None else None) if a.impl == "ours" else 0,

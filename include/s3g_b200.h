@@ -425,6 +425,16 @@ int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, cons
                             const float* weights, const double* sums, const void* workspace,
                             float* g_image, float* g_depth, void* stream);
 
+/* The same terms with lambda_dssim == 0 (train.py:417 skips SSIM then): sums[1] = 0, no derivative maps;
+ * workspace: 256 + 16 * 592 * 4 bytes are enough (s3g_image_loss_workspace_bytes(...) is an upper bound). */
+int s3g_image_l1_depth_forward(int B, int C, int H, int W, const float* image, const float* gt_image,
+                               const float* depth, const float* gt_depth, float max_depth,
+                               double* sums, void* workspace, void* stream);
+int s3g_image_l1_depth_backward(int B, int C, int H, int W, const float* image, const float* gt_image,
+                                const float* depth, const float* gt_depth, float max_depth,
+                                const float* weights, const double* sums, float* g_image, float* g_depth,
+                                void* stream);
+
 /* ---- HexPlane regularisers -------------------------------------------
  * s3g_plane_reg_*  <- GaussianModel.compute_regulation                 scene/gaussian_model.py:710-749
  *                     + compute_plane_smoothness                        scene/regulation.py:22-28

@@ -62,6 +62,8 @@ SIGNATURES = {
     "s3g_densify_stats": (_I, [_I, _V, _V, _V, _V, _V, _V]),
     "s3g_image_loss_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "s3g_image_loss_forward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V]),
+    "s3g_image_l1_depth_forward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V]),
+    "s3g_image_l1_depth_backward": (_I, [_I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _V, _V, _V, _V]),
     "s3g_knn_workspace_bytes": (_SZ, [_I]),
     "s3g_knn_mean_dist2": (_I, [_I, _V, _V, _V, _V]),
     "s3g_peer_reduce_scatter": (_I, [_I, _I, _V, _I64, _V]),

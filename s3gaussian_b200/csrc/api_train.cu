@@ -138,6 +138,51 @@ int s3g_image_loss_forward(int B, int C, int H, int W, const float* image, const
     return S3G_OK;
 }
 
+// ---- the same terms without SSIM (lambda_dssim == 0) ---------------------------------------------------------
+int s3g_image_l1_depth_forward(int B, int C, int H, int W, const float* image, const float* gt_image, const float* depth,
+                               const float* gt_depth, float max_depth, double* sums, void* workspace, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = loss_check(B, C, H, W, image, gt_image, depth, gt_depth)) return rc;
+    if (!sums || !workspace) return fail(S3G_ERR_ARG, "image_l1_depth_forward: null sums/workspace");
+    float* ws = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* part_img = ws;
+    float* part_dep = ws + 2 * kDepthBlocks;
+    int nimg = 0, ndep = 0;
+    if (C > 0) {
+        nimg = kDepthBlocks;
+        loss_l1_stats_kernel<<<kDepthBlocks, LOSS_THREADS, 0, stream>>>((size_t)B * C * H * W, image, gt_image, part_img);
+        S3G_CUDA(cudaGetLastError(), "loss_l1_stats launch");
+    }
+    if (depth) {
+        ndep = kDepthBlocks;
+        loss_depth_stats_kernel<<<kDepthBlocks, LOSS_THREADS, 0, stream>>>((size_t)B * H * W, depth, gt_depth, max_depth, part_dep);
+        S3G_CUDA(cudaGetLastError(), "loss_depth_stats launch");
+    }
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(nimg, part_img, ndep, part_dep, sums);
+    S3G_CUDA(cudaGetLastError(), "loss_reduce launch");
+    return S3G_OK;
+}
+
+int s3g_image_l1_depth_backward(int B, int C, int H, int W, const float* image, const float* gt_image, const float* depth,
+                                const float* gt_depth, float max_depth, const float* weights, const double* sums,
+                                float* g_image, float* g_depth, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = loss_check(B, C, H, W, image, gt_image, depth, gt_depth)) return rc;
+    if (!weights || !sums || (C > 0 && !g_image) || (depth && !g_depth))
+        return fail(S3G_ERR_ARG, "image_l1_depth_backward: null pointer");
+    if (C > 0) {
+        const size_t n = (size_t)B * C * H * W;
+        loss_l1_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, image, gt_image, weights, 1.0f / (float)n, g_image);
+        S3G_CUDA(cudaGetLastError(), "loss_l1_grad launch");
+    }
+    if (depth) {
+        const size_t nd = (size_t)B * H * W;
+        loss_depth_grad_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, stream>>>(nd, depth, gt_depth, max_depth, weights, sums, g_depth);
+        S3G_CUDA(cudaGetLastError(), "loss_depth_grad launch");
+    }
+    return S3G_OK;
+}
+
 int s3g_image_loss_backward(int B, int C, int H, int W, const float* image, const float* gt_image, const float* depth,
                             const float* gt_depth, float max_depth, const float* weights, const double* sums,
                             const void* workspace, float* g_image, float* g_depth, void* stream_) {

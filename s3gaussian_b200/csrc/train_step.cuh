@@ -215,6 +215,40 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_stats_kernel(int H, int W, 
     if (threadIdx.x == 0) partial[(size_t)bid * 2 + 1] = t2;
 }
 
+// L1 term only (lambda_dssim == 0: train.py:417 skips SSIM then): partial[b] = {sum|x-y|, 0}; n = B*C*H*W
+__global__ void __launch_bounds__(LOSS_THREADS) loss_l1_stats_kernel(size_t n, const float* __restrict__ x,
+                                                                    const float* __restrict__ y,
+                                                                    float* __restrict__ partial) {
+    __shared__ float red[8];
+    float s = 0.f;
+    const size_t n4 = n / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (vec) {
+        for (size_t i = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * LOSS_THREADS) {
+            const float4 a = __ldg(x4 + i), b = __ldg(y4 + i);
+            s += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+        }
+        for (size_t i = n4 * 4 + (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * LOSS_THREADS)
+            s += fabsf(x[i] - y[i]);
+    } else {
+        for (size_t i = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * LOSS_THREADS)
+            s += fabsf(x[i] - y[i]);
+    }
+    const float t1 = block_sum_256(s, red);
+    if (threadIdx.x == 0) { partial[(size_t)blockIdx.x * 2 + 0] = t1; partial[(size_t)blockIdx.x * 2 + 1] = 0.f; }
+}
+// dL/dx = wts[0]/N * sign(x-y)
+__global__ void __launch_bounds__(256) loss_l1_grad_kernel(size_t n, const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ wts, float invN, float* __restrict__ g) {
+    const float k = __ldg(wts) * invN;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float d = x[i] - y[i];
+    g[i] = d > 0.f ? k : (d < 0.f ? -k : 0.f);
+}
+
 // depth term statistics: partial[b] = {sum sq err over valid, #valid}; n = B*H*W
 __global__ void __launch_bounds__(LOSS_THREADS) loss_depth_stats_kernel(size_t n, const float* __restrict__ pred,
                                                                        const float* __restrict__ gt, float max_depth,

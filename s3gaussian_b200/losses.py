@@ -35,7 +35,7 @@ def _as4(t: torch.Tensor, what: str) -> torch.Tensor:
 
 class _ImageLossTerms(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, image, gt_image, depth, gt_depth, max_depth):
+    def forward(ctx, image, gt_image, depth, gt_depth, max_depth, with_ssim=True):
         lib = _lib.load()
         for t in (image, gt_image, depth, gt_depth):
             if t is not None and (not t.is_cuda or t.dtype != torch.float32):
@@ -56,11 +56,18 @@ class _ImageLossTerms(torch.autograd.Function):
             if d.numel() != B * H * W or g.numel() != B * H * W:
                 raise RuntimeError("image_loss_terms: depth / gt_depth must hold B*H*W values")
         dev = (x if x is not None else d).device
-        ws = torch.empty(lib.s3g_image_loss_workspace_bytes(B, Cc, H, W), dtype=torch.uint8, device=dev)
         sums = torch.empty(4, dtype=torch.float64, device=dev)
         ptr = lambda t: t.data_ptr() if t is not None else None
-        _lib.check(lib.s3g_image_loss_forward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), float(max_depth),
-                                              sums.data_ptr(), ws.data_ptr(), _stream()), "s3g_image_loss_forward")
+        if with_ssim:
+            ws = torch.empty(lib.s3g_image_loss_workspace_bytes(B, Cc, H, W), dtype=torch.uint8, device=dev)
+            _lib.check(lib.s3g_image_loss_forward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), float(max_depth),
+                                                  sums.data_ptr(), ws.data_ptr(), _stream()), "s3g_image_loss_forward")
+        else:       # lambda_dssim == 0: no stencil, no derivative maps
+            ws = torch.empty(256 + 16 * 592 * 4, dtype=torch.uint8, device=dev)
+            _lib.check(lib.s3g_image_l1_depth_forward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), float(max_depth),
+                                                      sums.data_ptr(), ws.data_ptr(), _stream()),
+                       "s3g_image_l1_depth_forward")
+        ctx.with_ssim = bool(with_ssim)
         n = float(max(B * Cc * H * W, 1))
         l1 = (sums[0] / n).float()
         ss = (sums[1] / n).float()
@@ -81,25 +88,31 @@ class _ImageLossTerms(torch.autograd.Function):
         gi = torch.empty_like(x) if x is not None else None
         gd = torch.empty_like(d) if d is not None else None
         ptr = lambda t: t.data_ptr() if t is not None else None
-        _lib.check(lib.s3g_image_loss_backward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), ctx.max_depth,
-                                               wts.data_ptr(), sums.data_ptr(), ws.data_ptr(), ptr(gi), ptr(gd),
-                                               _stream()), "s3g_image_loss_backward")
+        if ctx.with_ssim:
+            _lib.check(lib.s3g_image_loss_backward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), ctx.max_depth,
+                                                   wts.data_ptr(), sums.data_ptr(), ws.data_ptr(), ptr(gi), ptr(gd),
+                                                   _stream()), "s3g_image_loss_backward")
+        else:
+            _lib.check(lib.s3g_image_l1_depth_backward(B, Cc, H, W, ptr(x), ptr(y), ptr(d), ptr(g), ctx.max_depth,
+                                                       wts.data_ptr(), sums.data_ptr(), ptr(gi), ptr(gd), _stream()),
+                       "s3g_image_l1_depth_backward")
         return (gi.view(ctx.image_shape) if gi is not None else None, None,
-                gd.view(ctx.depth_shape) if gd is not None else None, None, None)
+                gd.view(ctx.depth_shape) if gd is not None else None, None, None, None)
 
 
-def image_loss_terms(image, gt_image, depth=None, gt_depth=None, max_depth: float = 80.0):
+def image_loss_terms(image, gt_image, depth=None, gt_depth=None, max_depth: float = 80.0, with_ssim: bool = True):
     """-> (mean|image-gt|, mean SSIM map, masked depth L2) as 0-d tensors; differentiable w.r.t.
     ``image`` and ``depth``.  image/gt: [C,H,W] or [B,C,H,W] (or both None: depth term only);
     depth/gt_depth: [..., H, W] holding B*H*W values (the reference squeezes them, loss_utils.py:29-30)
-    or both None."""
+    or both None.  with_ssim=False skips the SSIM stencil (the second value is 0), as train.py:417 does when
+    lambda_dssim == 0."""
     if (depth is None) != (gt_depth is None) or (image is None) != (gt_image is None):
         raise RuntimeError("image_loss_terms: image/gt_image and depth/gt_depth go in pairs")
     if image is None and depth is None:
         raise RuntimeError("image_loss_terms: nothing to compute")
     x = _as4(image, "image") if image is not None else None
     y = _as4(gt_image, "gt_image") if gt_image is not None else None
-    return _ImageLossTerms.apply(x, y, depth, gt_depth, max_depth)
+    return _ImageLossTerms.apply(x, y, depth, gt_depth, max_depth, with_ssim)
 
 
 # ---- the reference's function names (utils/loss_utils.py) -----------------------------------
@@ -121,5 +134,8 @@ def compute_depth(loss_type, pred_depth, gt_depth, max_depth: float = 80):
 
 def training_loss(image, gt_image, depth, gt_depth, lambda_dssim=0.2, lambda_depth=0.5, max_depth=80.0):
     """Ll1 + lambda_depth * depth_l2 + lambda_dssim * (1 - ssim): the image part of train.py:395-419."""
+    if lambda_dssim == 0:      # train.py:417: `if opt.lambda_dssim != 0` - the SSIM term is not even evaluated
+        l1, _, dl2 = image_loss_terms(image, gt_image, depth, gt_depth, max_depth, with_ssim=False)
+        return l1 + lambda_depth * dl2
     l1, ss, dl2 = image_loss_terms(image, gt_image, depth, gt_depth, max_depth)
     return l1 + lambda_dssim * (1.0 - ss) + lambda_depth * dl2

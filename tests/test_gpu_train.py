@@ -183,6 +183,21 @@ def test_image_loss_matches_reference_functions_on_gpu(built_lib):
     assert abs(ours.item() - ref.item()) < 1e-5
     assert rel(x.grad, xr.grad) < 1e-4
     assert rel(d.grad, dr.grad) < 1e-5
+    # lambda_dssim == 0 (train.py:418 does not evaluate SSIM then): the stencil-free kernels, odd sizes included
+    for shape in ((2, 3, 640, 960), (1, 3, 37, 53)):
+        img, gt, depth, gt_depth = [t.to(DEV) for t in mg.loss_inputs(*shape, 10)]
+        x = img.clone().requires_grad_(True)
+        d = depth.clone().requires_grad_(True)
+        ours = losses.training_loss(x, gt, d, gt_depth, lambda_dssim=0.0, lambda_depth=0.5)
+        ours.backward()
+        xr = img.clone().requires_grad_(True)
+        dr = depth.clone().requires_grad_(True)
+        ref = lu.l1_loss(xr, gt) + 0.5 * lu.compute_depth("l2", dr, gt_depth)
+        ref.backward()
+        assert abs(ours.item() - ref.item()) < 1e-6, shape
+        assert rel(x.grad, xr.grad) < 1e-6 and rel(d.grad, dr.grad) < 1e-5, shape
+        l1, ss, dl2 = losses.image_loss_terms(x, gt, d, gt_depth, with_ssim=False)
+        assert float(ss) == 0.0
 
 
 def test_plane_regulation_matches_reference_golden(built_lib):

@@ -459,8 +459,11 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {   // auxiliar
     return r;
 }
 
+// Register budget capped for 8 resident blocks per SM (64 registers, 20 spilled words): the kernel is HBM-bound and
+// gains from more loads in flight - 0.240 ms at 8 blocks, 0.244 at 6, 0.258 at the 5 the unconstrained 96 registers
+// allow (profiles/r02n_pbwd_ab.log; 2 M Gaussians).
 template <int MT, bool DP = false>   // MT = 16: compile-time SH row length; 0: runtime M.  DP: gradients go to a.sink
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_backward_kernel(const __grid_constant__ PreBwdArgs a) {
+__global__ void __launch_bounds__(PRE_THREADS, 8) preprocess_backward_kernel(const __grid_constant__ PreBwdArgs a) {
     extern __shared__ float s_dyn[];
     __shared__ Cam s_cam;
     load_cam(s_cam, a.view, a.proj, a.campos);

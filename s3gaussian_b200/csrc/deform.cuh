@@ -67,17 +67,23 @@ __device__ __forceinline__ void split_tf32_rna(float x, uint32_t& hi, uint32_t& 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
         "{%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-    mma_tf32(d, al, bh);   // small terms first
-    mma_tf32(d, ah, bl);
-    mma_tf32(d, ah, bh);
+
+// the three products of NT independent accumulators, interleaved so that consecutive HMMAs never depend on each other
+template <int NT>
+__device__ __forceinline__ void mma3_multi(float (&d)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[NT][2], const uint32_t (&bl)[NT][2]) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(d[j], al, bh[j]);   // small terms first
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(d[j], ah, bl[j]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(d[j], ah, bh[j]);
 }
 
 // Stage a PyTorch-layout weight [N][K] (row n contiguous) into smem rows of stride K+4.
@@ -109,24 +115,33 @@ __device__ __forceinline__ void cp_async16_w(void* smem, const void* gmem) {
 struct WPipe {
     float* buf[2];
     int cur, wi;
-    const WSeq* seq;
+    const WSeq* seq;     // shared-memory copy (a dynamically indexed kernel parameter is a long-scoreboard load)
     __device__ __forceinline__ void prefetch(int i, float* dst) const {
         const int K = seq->K[i], N = seq->N[i], WS = K + 4, k4n = K >> 2;
         const float* Wg = seq->W[i];
+        const bool pow2 = (k4n & (k4n - 1)) == 0;     // K = 64, 128, 256: a shift instead of an integer division
+        const int sh = __ffs(k4n) - 1;
         for (int e = threadIdx.x; e < N * k4n; e += DTHREADS) {
-            const int n = e / k4n, k4 = e - n * k4n;
+            const int n = pow2 ? (e >> sh) : e / k4n, k4 = e - n * k4n;
             cp_async16_w(dst + n * WS + 4 * k4, Wg + (size_t)n * K + 4 * k4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __device__ __forceinline__ void start() {   // kernel prologue
+    // kernel prologue: copies the sequence to shared memory, fetches layer 0 and ends with a barrier
+    __device__ __forceinline__ void start(const WSeq& src, WSeq* s_seq, float* b0, float* b1) {
+        for (int i = threadIdx.x; i < (int)(sizeof(WSeq) / 4); i += DTHREADS)
+            reinterpret_cast<uint32_t*>(s_seq)[i] = reinterpret_cast<const uint32_t*>(&src)[i];
+        __syncthreads();
+        seq = s_seq; buf[0] = b0; buf[1] = b1;
         cur = 0; wi = 0;
         prefetch(0, buf[0]);
-    }
-    // weights of layer `wi` are ready in the returned buffer; the next layer's are in flight
-    __device__ __forceinline__ float* acquire() {
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        release();
         __syncthreads();
+    }
+    // Weights of layer `wi` are in the returned buffer (the previous product's release() + barrier made them
+    // visible); the next layer's start flowing into the other buffer, which nobody reads any more since that
+    // same barrier.  No barrier of its own: one per product instead of two.
+    __device__ __forceinline__ float* acquire() {
         float* mine = buf[cur];
         const int nxt = (wi + 1 == seq->count) ? 0 : wi + 1;
         if (seq->W[nxt] != seq->W[wi]) {
@@ -136,6 +151,9 @@ struct WPipe {
         wi = nxt;
         return mine;
     }
+    // end of a product, immediately before its closing __syncthreads(): this thread's share of the next
+    // layer's weights has landed
+    __device__ __forceinline__ void release() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
 // out[g][n] = act_out( sum_k act_in(in[g][k]) * W[n][k] + b[n] ),  g < 64, n < N (N = 64 or 48).
@@ -157,6 +175,13 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
     for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     const float* rowA = sIn + (r0 + g) * inStride + t;
     const float* rowB = sIn + (r0 + g + 8) * inStride + t;
+    float bias[NTW][2];                  // fetched before the k loop so the epilogue does not wait on L2
+#pragma unroll
+    for (int j = 0; j < NTW; ++j) {
+        const int col = c0 + 8 * j + 2 * t;
+        bias[j][0] = active ? __ldg(bg + col) : 0.f;
+        bias[j][1] = active ? __ldg(bg + col + 1) : 0.f;
+    }
 #pragma unroll 4
     for (int k0 = 0; active && k0 < K; k0 += 8) {
         float a[4] = {rowA[k0], rowB[k0], rowA[k0 + 4], rowB[k0 + 4]};
@@ -166,20 +191,20 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
             if (RELU_IN) a[i] = fmaxf(a[i], 0.f);
             split_tf32(a[i], ah[i], al[i]);
         }
+        uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
         for (int j = 0; j < NTW; ++j) {
             const float* wr = sW + (c0 + 8 * j + g) * WS + k0 + t;
-            uint32_t bh[2], bl[2];
-            split_tf32(wr[0], bh[0], bl[0]);
-            split_tf32(wr[4], bh[1], bl[1]);
-            mma3(acc[j], ah, al, bh, bl);
+            split_tf32(wr[0], bh[j][0], bl[j][0]);
+            split_tf32(wr[4], bh[j][1], bl[j][1]);
         }
+        mma3_multi<NTW>(acc, ah, al, bh, bl);
     }
 #pragma unroll
     for (int j = 0; j < NTW; ++j) {
         if (!active) break;
         const int col = c0 + 8 * j + 2 * t;
-        const float b0 = __ldg(bg + col), b1 = __ldg(bg + col + 1);
+        const float b0 = bias[j][0], b1 = bias[j][1];
         float v0 = acc[j][0] + b0, v1 = acc[j][1] + b1, v2 = acc[j][2] + b0, v3 = acc[j][3] + b1;
         if (RELU_OUT) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
         sOut[(r0 + g) * outStride + col] = v0;
@@ -187,6 +212,7 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
         sOut[(r0 + g + 8) * outStride + col] = v2;
         sOut[(r0 + g + 8) * outStride + col + 1] = v3;
     }
+    pipe.release();
     __syncthreads();
 }
 
@@ -230,48 +256,24 @@ __device__ __forceinline__ AxisTap axis_tap(float x, int R) {
     return t;
 }
 
-// features of one Gaussian (this lane's channel) for all levels -> sFrow[32*l + lane]; two levels
-// (48 independent 128-byte loads) are in flight at a time.
-template <int LT>
-__device__ __forceinline__ void sample_gaussian(const DNet& n, const float ph[4], int lane, float* sFrow) {
-    const int L = LT > 0 ? LT : n.L;
-    for (int l0 = 0; l0 < L; l0 += 2) {
-        float v[2][6][4];
-        AxisTap ax[2][4];
-#pragma unroll
-        for (int dl = 0; dl < 2; ++dl) {
-            const int l = min(l0 + dl, L - 1);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) ax[dl][d] = axis_tap(ph[d], n.reso[l][d]);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int a = comb_a(k), b = comb_b(k);
-                const int W = n.reso[l][a];
-                const float* pl = n.planes[l][k] + lane;
-                // unsigned 32-bit texel offsets (planes are < 2^32 floats): one IMAD.WIDE.U32 per address
-                const int r0 = ax[dl][b].i0 * W, r1 = ax[dl][b].i1 * W;
-                v[dl][k][0] = __ldg(pl + (uint32_t)(r0 + ax[dl][a].i0) * FD);
-                v[dl][k][1] = __ldg(pl + (uint32_t)(r0 + ax[dl][a].i1) * FD);
-                v[dl][k][2] = __ldg(pl + (uint32_t)(r1 + ax[dl][a].i0) * FD);
-                v[dl][k][3] = __ldg(pl + (uint32_t)(r1 + ax[dl][a].i1) * FD);
-            }
-        }
-#pragma unroll
-        for (int dl = 0; dl < 2; ++dl) {
-            if (l0 + dl < L) {
-                float f = 1.f;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const AxisTap& X = ax[dl][comb_a(k)];
-                    const AxisTap& Y = ax[dl][comb_b(k)];
-                    const float s = (X.omf * Y.omf) * v[dl][k][0] + (X.f * Y.omf) * v[dl][k][1] +
-                                    (X.omf * Y.f) * v[dl][k][2] + (X.f * Y.f) * v[dl][k][3];
-                    f = (k == 0) ? s : f * s;     // interp_space = 1 * s0 * s1 * ... (hexplane.py:87-96)
-                }
-                sFrow[(l0 + dl) * FD + lane] = f;
-            }
-        }
-    }
+// ---- lane layout of the two plane kernels ------------------------------------------------
+// A warp works on FOUR Gaussians at a time: lane = (Gaussian sub = lane >> 3, channel quad q = lane & 7).  One
+// bilinear corner of the channels-last planes is one LDG.128 / RED.128 per lane, 8 lanes = the corner's 128-byte line.
+// Axis taps, texel offsets and bilinear weights are per Gaussian, so with one channel per lane (round 1) all 32 lanes
+// of a warp computed the same ones; with four channels per lane that overhead is amortised over 4x the data and
+// the load / RED instruction count drops 4x (both kernels were instruction-issue bound: 64-70 % issue-active).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void red4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+// bilinear sample of four channels; the expression tree is the one-channel version's, per component
+__device__ __forceinline__ void bilerp4(const AxisTap& X, const AxisTap& Y, const float4 (&v)[4], float (&s)[4]) {
+    const float w00 = X.omf * Y.omf, w01 = X.f * Y.omf, w10 = X.omf * Y.f, w11 = X.f * Y.f;
+    s[0] = w00 * v[0].x + w01 * v[1].x + w10 * v[2].x + w11 * v[3].x;
+    s[1] = w00 * v[0].y + w01 * v[1].y + w10 * v[2].y + w11 * v[3].y;
+    s[2] = w00 * v[0].z + w01 * v[1].z + w10 * v[2].z + w11 * v[3].z;
+    s[3] = w00 * v[0].w + w01 * v[1].w + w10 * v[2].w + w11 * v[3].w;
 }
 
 // SH basis (utils/sh_utils.py:57-112) for unit direction (x,y,z); returns count
@@ -320,20 +322,57 @@ struct SampleArgs {
 };
 template <int LT>
 __global__ void __launch_bounds__(256, 3) hexplane_sample_kernel(SampleArgs a) {
-    const int lane = threadIdx.x & 31;
+    const DNet& n = a.net;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, q4 = (lane & 7) * 4;
     const int wpb = blockDim.x >> 5;
-    const int FL = FD * a.net.L;
+    const int L = LT > 0 ? LT : n.L;
+    const int FL = FD * L;
     // Every block walks ONE contiguous run of Gaussians (its warps interleaved inside it): with the model kept in
     // a spatially coherent order (GaussianModel.spatial_sort, Morton curve) a block keeps revisiting the same few
     // texel lines while they are still in its SM's L1; in arbitrary order the assignment makes no difference.
     const int chunk = (a.P + gridDim.x - 1) / gridDim.x;
     const int g_begin = blockIdx.x * chunk, g_end = min(a.P, g_begin + chunk);
-    for (int g = g_begin + (threadIdx.x >> 5); g < g_end; g += wpb) {
+    for (int gb = g_begin + 4 * (threadIdx.x >> 5); gb < g_end; gb += 4 * wpb) {
+        const int gi = gb + sub;
+        const bool valid = gi < g_end;
+        const int gc = valid ? gi : g_end - 1;        // tail lanes repeat the last Gaussian and store nothing
         float ph[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)g * 3 + c) - a.net.aabb0[c]) * a.net.inv_span2[c] - 1.0f;
+        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gc * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
         ph[3] = a.time;
-        sample_gaussian<LT>(a.net, ph, lane, a.features + (size_t)g * FL);
+#pragma unroll
+        for (int l = 0; l < (LT > 0 ? LT : S3G_MAX_LEVELS); ++l) {
+            if (LT == 0 && l >= L) break;
+            AxisTap ax[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) ax[d] = axis_tap(ph[d], n.reso[l][d]);
+            float f[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {        // three planes = twelve 16-byte loads per lane in flight
+                float4 v[3][4];
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = 3 * h + kk, ca = comb_a(k), cb = comb_b(k);
+                    const int W = n.reso[l][ca];
+                    const float* pl = n.planes[l][k] + q4;
+                    // unsigned 32-bit texel offsets (planes are < 2^32 floats): one IMAD.WIDE.U32 per address
+                    const int r0 = ax[cb].i0 * W, r1 = ax[cb].i1 * W;
+                    v[kk][0] = ldg4(pl + (uint32_t)(r0 + ax[ca].i0) * FD);
+                    v[kk][1] = ldg4(pl + (uint32_t)(r0 + ax[ca].i1) * FD);
+                    v[kk][2] = ldg4(pl + (uint32_t)(r1 + ax[ca].i0) * FD);
+                    v[kk][3] = ldg4(pl + (uint32_t)(r1 + ax[ca].i1) * FD);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = 3 * h + kk;
+                    float sv[4];
+                    bilerp4(ax[comb_a(k)], ax[comb_b(k)], v[kk], sv);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) f[c] = (k == 0) ? sv[c] : f[c] * sv[c];   // interp_space = 1 * s0 * s1 * ... (hexplane.py:87-96)
+                }
+            }
+            if (valid) *reinterpret_cast<float4*>(a.features + (size_t)gi * FL + l * FD + q4) = make_float4(f[0], f[1], f[2], f[3]);
+        }
     }
 }
 
@@ -387,11 +426,9 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_forward_kernel(const __gri
     DeformSmem sm(s_dyn, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntiles = (a.P + DT - 1) / DT;
+    __shared__ WSeq s_seq;
     WPipe pipe;
-    pipe.seq = &a.wseq;
-    pipe.buf[0] = sm.W;
-    pipe.buf[1] = sm.W + HWID * (FS > HS ? FS : HS);
-    pipe.start();
+    pipe.start(a.wseq, &s_seq, sm.W, sm.W + HWID * (FS > HS ? FS : HS));
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * DT;
@@ -518,22 +555,26 @@ __device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WP
     float acc[NTW][4];
 #pragma unroll
     for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    const float* rowA = sIn + (r0 + g) * inStride + t;
-    const float* rowB = sIn + (r0 + g + 8) * inStride + t;
+    // The contraction index of an MMA can be permuted freely as long as A and B agree: fragment slots (t, t+4)
+    // take the physical indices (2t, 2t+1).  The weight reads W[n0+2t(+1)][c+g] then fall on banks 8t+g (+4)
+    // (row stride == 4 mod 32): conflict-free, where the natural slots gave 4t+g, two-way conflicts.
+    const float* rowA = sIn + (r0 + g) * inStride + 2 * t;
+    const float* rowB = sIn + (r0 + g + 8) * inStride + 2 * t;
 #pragma unroll 2
     for (int n0 = 0; n0 < N; n0 += 8) {
-        const float a[4] = {rowA[n0], rowB[n0], rowA[n0 + 4], rowB[n0 + 4]};
+        const float2 ra = *reinterpret_cast<const float2*>(rowA + n0), rb = *reinterpret_cast<const float2*>(rowB + n0);
+        const float a[4] = {ra.x, rb.x, ra.y, rb.y};
         uint32_t ah[4], al[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+        uint32_t bh[NTW][2], bl[NTW][2];
 #pragma unroll
         for (int j = 0; j < NTW; ++j) {
-            const float* wr = sW + (n0 + t) * WS + c0 + 8 * j + g;
-            uint32_t bh[2], bl[2];
-            split_tf32(wr[0], bh[0], bl[0]);
-            split_tf32(wr[4 * WS], bh[1], bl[1]);
-            mma3(acc[j], ah, al, bh, bl);
+            const float* wr = sW + (n0 + 2 * t) * WS + c0 + 8 * j + g;
+            split_tf32(wr[0], bh[j][0], bl[j][0]);
+            split_tf32(wr[WS], bh[j][1], bl[j][1]);
         }
+        mma3_multi<NTW>(acc, ah, al, bh, bl);
     }
 #pragma unroll
     for (int j = 0; j < NTW; ++j) {
@@ -551,6 +592,7 @@ __device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WP
             else { o[0] = v0; o[1] = v1; }
         }
     }
+    pipe.release();
     __syncthreads();
 }
 
@@ -571,21 +613,23 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
         for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll 2
         for (int k0 = 0; k0 < DT; k0 += 8) {
-            // A[m][k] = delta[k][m]
-            const float a[4] = {sDelta[(k0 + t) * dStride + m0 + g], sDelta[(k0 + t) * dStride + m0 + g + 8],
-                                sDelta[(k0 + t + 4) * dStride + m0 + g], sDelta[(k0 + t + 4) * dStride + m0 + g + 8]};
+            // A[m][k] = delta[k][m]; contraction slots (t, t+4) -> rows (2t, 2t+1) of the tile: banks 8t+g for
+            // every row stride == 4 (mod 32) or == 20 (mod 32) used here, conflict-free (see tile_linear_T)
+            const float* dr = sDelta + (k0 + 2 * t) * dStride + m0 + g;
+            const float a[4] = {dr[0], dr[8], dr[dStride], dr[dStride + 8]};
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+            uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                float b[2] = {sAct[(k0 + t) * aStride + n0 + 8 * j + g], sAct[(k0 + t + 4) * aStride + n0 + 8 * j + g]};
+                const float* ar = sAct + (k0 + 2 * t) * aStride + n0 + 8 * j + g;
+                float b[2] = {ar[0], ar[aStride]};
                 if (RELU_ACT) { b[0] = fmaxf(b[0], 0.f); b[1] = fmaxf(b[1], 0.f); }
-                uint32_t bh[2], bl[2];
-                split_tf32(b[0], bh[0], bl[0]);
-                split_tf32(b[1], bh[1], bl[1]);
-                mma3(acc[j], ah, al, bh, bl);
+                split_tf32(b[0], bh[j][0], bl[j][0]);
+                split_tf32(b[1], bh[j][1], bl[j][1]);
             }
+            mma3_multi<NT>(acc, ah, al, bh, bl);
         }
         // fire-and-forget REDs on the CTA-private partial buffer: a load-add-store would expose
         // one L2 round trip per output tile (measured: 14 ms of a 55 ms step)
@@ -702,11 +746,9 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
     const int ntiles = (a.P + DT - 1) / DT;
     float* part = a.partial + (size_t)blockIdx.x * a.off.total;
     for (int i = tid; i < a.off.total; i += DTHREADS) part[i] = 0.f;
+    __shared__ WSeq s_seq;
     WPipe pipe;
-    pipe.seq = &a.wseq;
-    pipe.buf[0] = sm.W;
-    pipe.buf[1] = sm.W + HWID * (FS > HS ? FS : HS);
-    pipe.start();
+    pipe.start(a.wseq, &s_seq, sm.W, sm.W + HWID * (FS > HS ? FS : HS));
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -848,6 +890,19 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         // ---- shs head + SH->RGB backward ---------------------------------------------
         {
             const bool on = n.shs.w1 != nullptr;
+            // the tile's [64][48] rows of shs and g_dshs are contiguous in global memory; they are fetched here, two
+            // products ahead of their use (read at the point of use they were 9 % of the kernel's stall samples)
+            constexpr int SPT = DT * 48 / DTHREADS;
+            float pre_shs[SPT], pre_gd[SPT];
+            {
+                const size_t base = (size_t)g0 * 48, lim = (size_t)a.P * 48;
+#pragma unroll
+                for (int i = 0; i < SPT; ++i) {
+                    const size_t idx = base + tid + i * DTHREADS;
+                    pre_shs[i] = idx < lim ? __ldg(a.shs + idx) : 0.f;
+                    pre_gd[i] = (a.g_dshs && idx < lim) ? __ldg(a.g_dshs + idx) : 0.f;
+                }
+            }
             if (on) {
                 tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
                 tile_linear<64, 48, false, false>(sm.A, HS, pipe, n.shs.b2, sm.Dout, 52);   // dshs
@@ -856,9 +911,10 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                 __syncthreads();
             }
             // shs_final = shs + dshs (in place)
-            for (int e = tid; e < DT * 48; e += DTHREADS) {
-                const int g = e / 48, j = e - 48 * g;
-                if (g0 + g < a.P) sm.Dout[g * 52 + j] += a.shs[(size_t)(g0 + g) * 48 + j];
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                const int e = tid + i * DTHREADS, g = e / 48, j = e - 48 * g;
+                if (g0 + g < a.P) sm.Dout[g * 52 + j] += pre_shs[i];
             }
             __syncthreads();
             // per Gaussian: colour clamp mask, dL/dshs_final = basis (x) g_col, dL/d(dir) -> d_xyz part (into G[11..13])
@@ -932,12 +988,13 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
             }
             __syncthreads();
             // d_shs (param) = dL/dshs_final ; delta of the head output = that + g_dshs
-            for (int e = tid; e < DT * 48; e += DTHREADS) {
-                const int g = e / 48, j = e - 48 * g;
+#pragma unroll
+            for (int i = 0; i < SPT; ++i) {
+                const int e = tid + i * DTHREADS, g = e / 48, j = e - 48 * g;
                 if (g0 + g < a.P) {
                     const float v = sm.Dout[g * 52 + j];
                     a.d_shs[(size_t)(g0 + g) * 48 + j] = v;
-                    sm.Dout[g * 52 + j] = v + ldz(a.g_dshs, (size_t)(g0 + g) * 48 + j);
+                    sm.Dout[g * 52 + j] = v + pre_gd[i];
                 } else {
                     sm.Dout[g * 52 + j] = 0.f;
                 }
@@ -1000,15 +1057,18 @@ template <int LT>
 __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a) {
     const DNet& n = a.net;
     const int L = LT > 0 ? LT : n.L;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, q = lane & 7, q4 = q * 4;   // see "lane layout" above
     const int wpb = blockDim.x >> 5;
     const int FL = FD * L;
     const int chunk = (a.P + gridDim.x - 1) / gridDim.x;      // contiguous run per block, see hexplane_sample_kernel
     const int g_begin = blockIdx.x * chunk, g_end = min(a.P, g_begin + chunk);
-    for (int gi = g_begin + (threadIdx.x >> 5); gi < g_end; gi += wpb) {
+    for (int gb = g_begin + 4 * (threadIdx.x >> 5); gb < g_end; gb += 4 * wpb) {
+        const int gi = gb + sub;
+        const bool valid = gi < g_end;
+        const int gc = valid ? gi : g_end - 1;
         float ph[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gi * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
+        for (int c = 0; c < 3; ++c) ph[c] = (__ldg(a.xyz + (size_t)gc * 3 + c) - n.aabb0[c]) * n.inv_span2[c] - 1.0f;
         ph[3] = a.time;
         float dph[3] = {0.f, 0.f, 0.f};    // this lane's share of dL/dp_hat
 #pragma unroll
@@ -1017,62 +1077,78 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
             AxisTap ax[4];
 #pragma unroll
             for (int d = 0; d < 4; ++d) ax[d] = axis_tap(ph[d], n.reso[l][d]);
-            float v[6][4], s[6];
+            float df[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                const float4 t = ldg4(a.dfeatures + (size_t)gi * FL + l * FD + q4);
+                df[0] = t.x; df[1] = t.y; df[2] = t.z; df[3] = t.w;
+            }
+            // pass 1 (k ascending): texel offsets and the prefix products pre[k] = s_0 * ... * s_{k-1}
             uint32_t o00[6], o01[6], o10[6], o11[6];      // unsigned 32-bit texel offsets: one IMAD.WIDE.U32 per address
+            float pre[6][4];
+            {
+                float run[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int ca = comb_a(k), cb = comb_b(k);
-                const int W = n.reso[l][ca];
-                const float* pl = n.planes[l][k] + lane;
-                const int r0 = ax[cb].i0 * W, r1 = ax[cb].i1 * W;
-                o00[k] = (uint32_t)(r0 + ax[ca].i0) * FD; o01[k] = (uint32_t)(r0 + ax[ca].i1) * FD;
-                o10[k] = (uint32_t)(r1 + ax[ca].i0) * FD; o11[k] = (uint32_t)(r1 + ax[ca].i1) * FD;
-                v[k][0] = __ldg(pl + o00[k]); v[k][1] = __ldg(pl + o01[k]);
-                v[k][2] = __ldg(pl + o10[k]); v[k][3] = __ldg(pl + o11[k]);
+                for (int k = 0; k < 6; ++k) {
+                    const int ca = comb_a(k), cb = comb_b(k);
+                    const int W = n.reso[l][ca];
+                    const float* pl = n.planes[l][k] + q4;
+                    const int r0 = ax[cb].i0 * W, r1 = ax[cb].i1 * W;
+                    o00[k] = (uint32_t)(r0 + ax[ca].i0) * FD; o01[k] = (uint32_t)(r0 + ax[ca].i1) * FD;
+                    o10[k] = (uint32_t)(r1 + ax[ca].i0) * FD; o11[k] = (uint32_t)(r1 + ax[ca].i1) * FD;
+                    const float4 v[4] = {ldg4(pl + o00[k]), ldg4(pl + o01[k]), ldg4(pl + o10[k]), ldg4(pl + o11[k])};
+                    float sv[4];
+                    bilerp4(ax[ca], ax[cb], v, sv);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { pre[k][c] = run[c]; run[c] *= sv[c]; }
+                }
             }
-            const float df = __ldg(a.dfeatures + (size_t)gi * FL + l * FD + lane);
+            // pass 2 (k descending, running suffix product): ds_k = df * prod_{j != k} s_j.  The corner values are
+            // read again (L1 hits) instead of being kept: 96 registers per level would not fit.
+            float suf[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const AxisTap& X = ax[comb_a(k)];
-                const AxisTap& Y = ax[comb_b(k)];
-                s[k] = (X.omf * Y.omf) * v[k][0] + (X.f * Y.omf) * v[k][1] + (X.omf * Y.f) * v[k][2] +
-                       (X.f * Y.f) * v[k][3];
-            }
-            // prefix / suffix products: ds_k = df * prod_{j != k} s_j
-            float pre[6], suf[6];
-            pre[0] = 1.f;
-#pragma unroll
-            for (int k = 1; k < 6; ++k) pre[k] = pre[k - 1] * s[k - 1];
-            suf[5] = 1.f;
-#pragma unroll
-            for (int k = 4; k >= 0; --k) suf[k] = suf[k + 1] * s[k + 1];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 5; k >= 0; --k) {
                 const int ca = comb_a(k), cb = comb_b(k);
                 const AxisTap& X = ax[ca];
                 const AxisTap& Y = ax[cb];
-                const float ds = df * pre[k] * suf[k];
-                float* gp = a.gplanes[l][k] + lane;
+                const float* pl = n.planes[l][k] + q4;
+                const float4 v[4] = {ldg4(pl + o00[k]), ldg4(pl + o01[k]), ldg4(pl + o10[k]), ldg4(pl + o11[k])};
+                float sv[4], ds[4];
+                bilerp4(X, Y, v, sv);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { ds[c] = df[c] * pre[k][c] * suf[c]; suf[c] *= sv[c]; }
                 // a border-clamped neighbour carries weight exactly 0 and aliases a valid texel: adding
                 // 0.0 leaves it unchanged, so the four REDs are unconditional (no branches in the loop)
-                const float wx0 = X.omf * ds, wx1 = X.f * ds;
-                atomicAdd(gp + o00[k], wx0 * Y.omf);
-                atomicAdd(gp + o01[k], wx1 * Y.omf);
-                atomicAdd(gp + o10[k], wx0 * Y.f);
-                atomicAdd(gp + o11[k], wx1 * Y.f);
+                if (valid) {
+                    float* gp = a.gplanes[l][k] + q4;
+                    float wx0[4], wx1[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { wx0[c] = X.omf * ds[c]; wx1[c] = X.f * ds[c]; }
+                    red4(gp + o00[k], wx0[0] * Y.omf, wx0[1] * Y.omf, wx0[2] * Y.omf, wx0[3] * Y.omf);
+                    red4(gp + o01[k], wx1[0] * Y.omf, wx1[1] * Y.omf, wx1[2] * Y.omf, wx1[3] * Y.omf);
+                    red4(gp + o10[k], wx0[0] * Y.f, wx0[1] * Y.f, wx0[2] * Y.f, wx0[3] * Y.f);
+                    red4(gp + o11[k], wx1[0] * Y.f, wx1[1] * Y.f, wx1[2] * Y.f, wx1[3] * Y.f);
+                }
                 // d(sample)/d(ix), d(sample)/d(iy)
-                const float dsx = (v[k][1] - v[k][0]) * Y.omf + (v[k][3] - v[k][2]) * Y.f;
-                const float dsy = (v[k][2] - v[k][0]) * X.omf + (v[k][3] - v[k][1]) * X.f;
-                if (ca < 3) dph[ca] += ds * dsx * X.g;
-                if (cb < 3) dph[cb] += ds * dsy * Y.g;
+                const float vv[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
+                                        {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float dsx = (vv[1][c] - vv[0][c]) * Y.omf + (vv[3][c] - vv[2][c]) * Y.f;
+                    const float dsy = (vv[2][c] - vv[0][c]) * X.omf + (vv[3][c] - vv[1][c]) * X.f;
+                    if (ca < 3) dph[ca] += ds[c] * dsx * X.g;
+                    if (cb < 3) dph[cb] += ds[c] * dsy * Y.g;
+                }
             }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dph[c] += __shfl_xor_sync(0xffffffffu, dph[c], o);
+            for (int o = 4; o > 0; o >>= 1) dph[c] += __shfl_xor_sync(0xffffffffu, dph[c], o);   // the Gaussian's 8 lanes
         }
-        if (lane < 3) a.d_xyz[(size_t)gi * 3 + lane] += dph[lane] * n.inv_span2[lane];
+        if (valid && q < 3) {
+            const float d = q == 0 ? dph[0] : (q == 1 ? dph[1] : dph[2]);
+            a.d_xyz[(size_t)gi * 3 + q] += d * n.inv_span2[q];
+        }
     }
 }
 

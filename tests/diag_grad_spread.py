@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--runs", type=int, default=4)
     a = ap.parse_args()
     import util
-    from oracle import ref_ext
+    import ref_ext
     from s3gaussian_b200 import synthetic as syn, diff_gaussian_rasterization as ours
     from test_gpu_raster import bench_camera
     ref = ref_ext.load()

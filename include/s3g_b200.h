@@ -344,6 +344,20 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
 /* bytes of `workspace` for s3g_deform_forward (tensor-core-ready copies of the Linear weights) */
 size_t s3g_deform_forward_workspace_bytes(const s3g_deform_net* net);
 
+/* Training variant: the same forward, which also keeps the decoder's hidden activations (h = feature_out(f) and the
+ * hidden layer of every enabled head, scene/deformation.py:56-76 - what autograd keeps for the reference) in the
+ * opaque buffer `acts` of s3g_deform_saved_bytes(net, P) bytes, so that s3g_deform_backward_saved does not
+ * recompute them.  s3g_deform_saved_bytes is 0 for nets whose forward does not run on the tcgen05 kernel (more
+ * than 4 levels); such nets use s3g_deform_forward / s3g_deform_backward.  acts == NULL: identical to
+ * s3g_deform_forward. */
+size_t s3g_deform_saved_bytes(const s3g_deform_net* net, int P);
+int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                            const float* rotations, const float* opacity, const float* shs, float time,
+                            const float* campos, int sh_degree,
+                            float* means3D, float* scales_act, float* rot_act, float* opacity_act,
+                            float* colors, float* dx, float* dshs, float* feat, float* features, float* acts,
+                            void* workspace, void* stream);
+
 /* Backward of the above.  g_* are dL/d(output) (NULL = zero).  Writes dL/d(raw inputs)
  * [P,*] in full, overwrites the Linear gradients in `grads` and accumulates the plane
  * gradients.  `features` is the buffer the forward filled.  `workspace` must hold
@@ -357,6 +371,15 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
                         const float* g_dshs, const float* g_feat,
                         float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
                         const s3g_deform_net_grads* grads, void* workspace, void* stream);
+/* Same with the hidden activations s3g_deform_forward_save stored (acts == NULL: recompute, as above). */
+int s3g_deform_backward_saved(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                              const float* rotations, const float* opacity, const float* shs, float time,
+                              const float* campos, int sh_degree, const float* features, const float* acts,
+                              const float* g_means3D, const float* g_scales_act, const float* g_rot_act,
+                              const float* g_opacity_act, const float* g_colors, const float* g_dx,
+                              const float* g_dshs, const float* g_feat,
+                              float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
+                              const s3g_deform_net_grads* grads, void* workspace, void* stream);
 
 /* ---- tcgen05 building-block self-test (csrc/umma_test.cu) -----------------
  * D[128,N] = A[128,K] * B[N,K]^T on the 5th-gen tensor cores (kind::tf32, accumulators in TMEM),

@@ -40,6 +40,15 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
                        const float* campos, int sh_degree, float* means3D, float* scales_act,
                        float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
                        float* feat, float* features, void* workspace, void* stream_) {
+    return s3g_deform_forward_save(net, P, xyz, scales, rotations, opacity, shs, time, campos, sh_degree, means3D, scales_act,
+                                   rot_act, opacity_act, colors, dx, dshs, feat, features, nullptr, workspace, stream_);
+}
+
+int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                            const float* rotations, const float* opacity, const float* shs, float time,
+                            const float* campos, int sh_degree, float* means3D, float* scales_act,
+                            float* rot_act, float* opacity_act, float* colors, float* dx, float* dshs,
+                            float* feat, float* features, float* acts, void* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
     if (P == 0) return S3G_OK;
@@ -75,6 +84,13 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
         t.campos = campos; t.sh_degree = sh_degree;
         t.o_means = means3D; t.o_scales = scales_act; t.o_rot = rot_act; t.o_opacity = opacity_act; t.o_colors = colors;
         t.o_dx = dx; t.o_dshs = dshs; t.o_feat = feat; t.features = features;
+        t.acts = acts;
+        t.act_stride = (size_t)((P + 127) / 128) * 128 * 64;
+        {
+            int slot[AK_COUNT];
+            act_slots(a.net, slot);
+            for (int i = 0; i < AK_COUNT; ++i) t.act_slot[i] = slot[i];
+        }
         TcPrepArgs pp;
         build_tc_table(a.net, t.tab, &pp);
         pp.tab = t.tab;
@@ -87,6 +103,7 @@ int s3g_deform_forward(const s3g_deform_net* net, int P, const float* xyz, const
         const int ntiles = (P + TCM - 1) / TCM;
         deform_forward_tc_kernel<<<deform_grid(ntiles), TCM, smem, stream>>>(t);
     } else {
+        if (acts) return fail(S3G_ERR_ARG, "deform_forward: this net's forward stores no activations (s3g_deform_saved_bytes == 0)");
         const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
         const int ntiles = (P + DT - 1) / DT;
         S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");

@@ -27,10 +27,24 @@ int bwd_grid(int ntiles) {
     return ntiles < sms ? ntiles : sms;
 }
 constexpr int kMaxBwdGrid = 256;
+// per-texel accumulators of the time planes (ScatterArgs::tacc): [level][axis][reso][32] floats
+size_t tacc_floats(const DNet& d) {
+    size_t t = 0;
+    for (int l = 0; l < d.L; ++l)
+        for (int ax = 0; ax < 3; ++ax) t += (size_t)d.reso[l][ax] * FD;
+    return t;
+}
 
 }  // namespace
 
 extern "C" {
+
+size_t s3g_deform_saved_bytes(const s3g_deform_net* net, int P) {
+    DNet d;
+    if (to_dnet(net, d) != S3G_OK || P <= 0) return 0;
+    int slot[AK_COUNT];
+    return (size_t)act_slots(d, slot) * ((size_t)((P + 127) / 128) * 128 * 64) * sizeof(float);
+}
 
 size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
     DNet d;
@@ -38,7 +52,9 @@ size_t s3g_deform_workspace_bytes(const s3g_deform_net* net, int P) {
     GradOff o;
     make_offsets(d, o);
     // per-CTA partial Linear gradients + dL/d(features) [P][32L]
-    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float) + 256;
+    // + the time planes' per-texel accumulators
+    return (size_t)kMaxBwdGrid * o.total * sizeof(float) + 512 + (size_t)(P > 0 ? P : 0) * FD * d.L * sizeof(float) + 256 +
+           tacc_floats(d) * sizeof(float) + 256;
 }
 
 int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
@@ -48,6 +64,18 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
                         const float* g_colors, const float* g_dx, const float* g_dshs, const float* g_feat,
                         float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
                         const s3g_deform_net_grads* grads, void* workspace, void* stream_) {
+    return s3g_deform_backward_saved(net, P, xyz, scales, rotations, opacity, shs, time, campos, sh_degree, features, nullptr,
+                                     g_means3D, g_scales_act, g_rot_act, g_opacity_act, g_colors, g_dx, g_dshs, g_feat,
+                                     d_xyz, d_scales, d_rotations, d_opacity, d_shs, grads, workspace, stream_);
+}
+
+int s3g_deform_backward_saved(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
+                              const float* rotations, const float* opacity, const float* shs, float time,
+                              const float* campos, int sh_degree, const float* features, const float* acts,
+                              const float* g_means3D, const float* g_scales_act, const float* g_rot_act, const float* g_opacity_act,
+                              const float* g_colors, const float* g_dx, const float* g_dshs, const float* g_feat,
+                              float* d_xyz, float* d_scales, float* d_rotations, float* d_opacity, float* d_shs,
+                              const s3g_deform_net_grads* grads, void* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0) return fail(S3G_ERR_ARG, "deform_backward: P < 0");
     DeformBwdArgs a;
@@ -71,7 +99,12 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
             if (!a.gplanes[l][k]) return fail(S3G_ERR_ARG, "deform_backward: null plane gradient");
         }
     make_offsets(d, a.off);
-    build_wseq(d, true, a.wseq);
+    const bool saved = acts != nullptr && act_slots(d, a.act_slot) > 0;
+    if (acts && !saved) return fail(S3G_ERR_ARG, "deform_backward: this net's forward stores no activations (s3g_deform_saved_bytes == 0)");
+    if (!saved) act_slots(d, a.act_slot);
+    a.acts = saved ? acts : nullptr;
+    a.act_stride = (size_t)((P + 127) / 128) * 128 * 64;
+    build_wseq(d, true, a.wseq, saved);
     a.partial = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     a.features = features;
     a.dfeatures = a.partial + (size_t)kMaxBwdGrid * a.off.total;
@@ -103,25 +136,43 @@ int s3g_deform_backward(const s3g_deform_net* net, int P, const float* xyz, cons
     if (P > 0) {
         const size_t smem = DeformBwdSmem::floats(d.L) * sizeof(float);
         if (smem > 227 * 1024) return fail(S3G_ERR_UNSUPPORTED, "deform_backward: too many levels for shared memory");
-        if (d.L == 4) {
-            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
-            deform_backward_kernel<4><<<grid, DTHREADS, smem, stream>>>(a);
-        } else {
-            S3G_CUDA(cudaFuncSetAttribute(deform_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
-            deform_backward_kernel<0><<<grid, DTHREADS, smem, stream>>>(a);
-        }
+        auto launch = [&](auto kernel) -> int {
+            S3G_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform bwd smem attr");
+            kernel<<<grid, DTHREADS, smem, stream>>>(a);
+            return S3G_OK;
+        };
+        if (saved) rc = d.L == 4 ? launch(deform_backward_kernel<4, true>) : launch(deform_backward_kernel<0, true>);
+        else rc = d.L == 4 ? launch(deform_backward_kernel<4, false>) : launch(deform_backward_kernel<0, false>);
+        if (rc != S3G_OK) return rc;
         S3G_CUDA(cudaGetLastError(), "deform_backward launch");
         ScatterArgs sc;
         sc.net = a.net; sc.P = P; sc.xyz = xyz; sc.time = time; sc.dfeatures = a.dfeatures; sc.d_xyz = d_xyz;
         for (int l = 0; l < S3G_MAX_LEVELS; ++l)
             for (int k = 0; k < 6; ++k) sc.gplanes[l][k] = l < d.L ? a.gplanes[l][k] : nullptr;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int blocks = std::min((P + 7) / 8, sms * 8);
-        if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
-        else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
-        S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
+        TimeRowsArgs tr;
+        tr.net = a.net; tr.time = time;
+        {
+            float* tacc = reinterpret_cast<float*>(((uintptr_t)(a.dfeatures + (size_t)P * FD * d.L) + 255) & ~(uintptr_t)255);
+            S3G_CUDA(cudaMemsetAsync(tacc, 0, tacc_floats(d) * sizeof(float), stream), "deform bwd memset (time-plane sums)");
+            int maxw = 1;
+            for (int l = 0; l < S3G_MAX_LEVELS; ++l)
+                for (int ax = 0; ax < 3; ++ax) {
+                    sc.tacc[l][ax] = l < d.L ? tacc : nullptr;
+                    tr.tacc[l][ax] = sc.tacc[l][ax];
+                    if (l < d.L) { tacc += (size_t)d.reso[l][ax] * FD; maxw = std::max(maxw, d.reso[l][ax]); }
+                }
+            for (int l = 0; l < S3G_MAX_LEVELS; ++l)
+                for (int k = 0; k < 6; ++k) tr.gplanes[l][k] = sc.gplanes[l][k];
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int blocks = std::min((P + 7) / 8, sms * 8);
+            if (d.L == 4) hexplane_scatter_kernel<4><<<blocks, 256, 0, stream>>>(sc);
+            else hexplane_scatter_kernel<0><<<blocks, 256, 0, stream>>>(sc);
+            S3G_CUDA(cudaGetLastError(), "hexplane_scatter launch");
+            hexplane_time_rows_kernel<<<dim3((maxw * FD + 255) / 256, 3, d.L), 256, 0, stream>>>(tr);
+            S3G_CUDA(cudaGetLastError(), "hexplane_time_rows launch");
+        }
     }
     {
         int maxc = 1;

@@ -114,11 +114,14 @@ __device__ __forceinline__ void cp_async16_w(void* smem, const void* gmem) {
 }
 struct WPipe {
     float* buf[2];
-    int cur, wi;
+    int cur, wi, count;
     const WSeq* seq;     // shared-memory copy (a dynamically indexed kernel parameter is a long-scoreboard load)
-    __device__ __forceinline__ void prefetch(int i, float* dst) const {
-        const int K = seq->K[i], N = seq->N[i], WS = K + 4, k4n = K >> 2;
-        const float* Wg = seq->W[i];
+    // descriptor of layer wi + 1, read one product ahead of its use so that acquire() never waits on it
+    const float* nW;
+    int nK, nN;
+    bool nNew;           // layer wi + 1 uses other weights than layer wi
+    __device__ __forceinline__ void prefetch(const float* Wg, int K, int N, float* dst) const {
+        const int WS = K + 4, k4n = K >> 2;
         const bool pow2 = (k4n & (k4n - 1)) == 0;     // K = 64, 128, 256: a shift instead of an integer division
         const int sh = __ffs(k4n) - 1;
         for (int e = threadIdx.x; e < N * k4n; e += DTHREADS) {
@@ -127,14 +130,20 @@ struct WPipe {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    __device__ __forceinline__ void load_next() {
+        const int nxt = (wi + 1 == count) ? 0 : wi + 1;
+        nW = seq->W[nxt]; nK = seq->K[nxt]; nN = seq->N[nxt];
+        nNew = nW != seq->W[wi];
+    }
     // kernel prologue: copies the sequence to shared memory, fetches layer 0 and ends with a barrier
     __device__ __forceinline__ void start(const WSeq& src, WSeq* s_seq, float* b0, float* b1) {
         for (int i = threadIdx.x; i < (int)(sizeof(WSeq) / 4); i += DTHREADS)
             reinterpret_cast<uint32_t*>(s_seq)[i] = reinterpret_cast<const uint32_t*>(&src)[i];
         __syncthreads();
         seq = s_seq; buf[0] = b0; buf[1] = b1;
-        cur = 0; wi = 0;
-        prefetch(0, buf[0]);
+        cur = 0; wi = 0; count = s_seq->count;
+        prefetch(s_seq->W[0], s_seq->K[0], s_seq->N[0], buf[0]);
+        load_next();
         release();
         __syncthreads();
     }
@@ -143,12 +152,12 @@ struct WPipe {
     // same barrier.  No barrier of its own: one per product instead of two.
     __device__ __forceinline__ float* acquire() {
         float* mine = buf[cur];
-        const int nxt = (wi + 1 == seq->count) ? 0 : wi + 1;
-        if (seq->W[nxt] != seq->W[wi]) {
-            prefetch(nxt, buf[cur ^ 1]);
+        if (nNew) {
+            prefetch(nW, nK, nN, buf[cur ^ 1]);
             cur ^= 1;
         }
-        wi = nxt;
+        wi = (wi + 1 == count) ? 0 : wi + 1;
+        load_next();
         return mine;
     }
     // end of a product, immediately before its closing __syncthreads(): this thread's share of the next
@@ -695,6 +704,9 @@ struct DeformBwdArgs {
     float* gplanes[S3G_MAX_LEVELS][6];
     float* partial;      // [gridDim.x][off.total]
     const float* features;   // [P][32L] from the forward
+    const float* acts;       // hidden activations kept by the tcgen05 forward (SAVED kernels; layout: DeformTcArgs::acts), else NULL
+    int act_slot[8];         // deform_host.cuh: AK_H, AK_POS, AK_SCL, AK_ROT, AK_OPA, AK_SHS, AK_D0, AK_D2; -1 = absent
+    size_t act_stride;       // floats per slot = ceil(P / 128) * 128 * 64
     float* dfeatures;        // [P][32L] dL/d(features), consumed by hexplane_scatter_kernel
     GradOff off;
     WSeq wseq;
@@ -726,6 +738,31 @@ struct DeformBwdSmem {
 
 __device__ __forceinline__ float ldz(const float* p, size_t i) { return p ? p[i] : 0.f; }
 
+// [64][FL] rows of a per-Gaussian array -> smem rows of stride FS with cp.async (rows past P are zero-filled);
+// completion: the caller's cp.async.wait_all (WPipe::release) + barrier
+__device__ __forceinline__ void tile_rows_async(const float* __restrict__ gsrc, int g0, int P, int FL, float* sDst, int FS) {
+    const int n4 = FL >> 2;
+    for (int i = threadIdx.x; i < DT * n4; i += DTHREADS) {
+        const int g = i / n4, c4 = i - g * n4;
+        const bool ok = g0 + g < P;
+        const float* src = gsrc + (size_t)(ok ? g0 + g : 0) * FL + 4 * c4;
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sDst + g * FS + 4 * c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One 64-row half of a kept 128 x 64 operand tile (deform_tc.cuh) -> smem rows of stride FS.  The tile is stored in the
+// tensor core's K-major core-matrix order: 16-byte piece i of the half holds columns 4*((i >> 3) & 15) .. +3 of row
+// 8 * (i >> 7) + (i & 7).  The 16 KB are contiguous in global memory, so the copy is fully coalesced.
+__device__ __forceinline__ void tile_canon_async(const float* __restrict__ half, float* sDst, int FS) {
+    for (int i = threadIdx.x; i < DT * 16; i += DTHREADS) {
+        const int r = ((i >> 7) << 3) + (i & 7), kq = (i >> 3) & 15;
+        cp_async16_w(sDst + r * FS + 4 * kq, half + 4 * i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int KF>   // KF = 32*L
 __device__ __forceinline__ void feat_layers_bwd(const DeformBwdSmem& sm, const DNet& n, float* part, const GradOff& off,
                                                 int FS, WPipe& pipe) {
@@ -735,7 +772,10 @@ __device__ __forceinline__ void feat_layers_bwd(const DeformBwdSmem& sm, const D
     tile_linear_T<KF, 64, TL_ASSIGN>(sm.DH, HS, pipe, sm.A, FS, nullptr, 0);
 }
 
-template <int LT>
+// SAVED: the hidden activations (h and every head's hidden layer) come from the buffer the tcgen05 forward filled
+// instead of being recomputed - a third of the tile's MMA products and their barriers disappear; the tiles arrive by
+// cp.async one head ahead of their use, alternating between the two activation buffers.
+template <int LT, bool SAVED>
 __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __grid_constant__ DeformBwdArgs a) {
     extern __shared__ __align__(16) float s_dyn[];
     const DNet& n = a.net;
@@ -750,6 +790,25 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
     WPipe pipe;
     pipe.start(a.wseq, &s_seq, sm.W, sm.W + HWID * (FS > HS ? FS : HS));
     __syncthreads();
+    // SAVED: which of the two activation buffers each stored tile lands in (consecutive enabled kinds alternate)
+    const bool on_pos = n.pos.w1, on_scl = n.scl.w1, on_rot = n.rot.w1, on_opa = n.opa.w1, on_shs = n.shs.w1, on_d = n.w_d0;
+    float* abuf[8];
+    {
+        int j = 0;
+        const bool en[8] = {false, on_pos, on_scl, on_rot, on_opa, on_shs, on_d, on_d};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { abuf[k] = (j & 1) ? sm.B : sm.A; if (en[k]) ++j; }
+    }
+#define S3G_FETCH_ACT(KIND) tile_canon_async(a.acts + (size_t)a.act_slot[KIND] * a.act_stride + (size_t)g0 * 64, abuf[KIND], HS)
+    // start the load of the first enabled activation kind after `kind` (a compile-time constant at every call)
+    auto fetch_after = [&](int kind, int g0) {
+        if (kind < 1 && on_pos) S3G_FETCH_ACT(1);
+        else if (kind < 2 && on_scl) S3G_FETCH_ACT(2);
+        else if (kind < 3 && on_rot) S3G_FETCH_ACT(3);
+        else if (kind < 4 && on_opa) S3G_FETCH_ACT(4);
+        else if (kind < 5 && on_shs) S3G_FETCH_ACT(5);
+        else if (kind < 6 && on_d) S3G_FETCH_ACT(6);
+    };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * DT;
@@ -759,6 +818,14 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         }
         for (int i = tid; i < DT * HS; i += DTHREADS) sm.DH[i] = 0.f;
         __syncthreads();
+        if (SAVED) {
+            // ---- h, the features (for the last product pair) and the first head's hidden layer: stored by the forward
+            tile_canon_async(a.acts + (size_t)a.act_slot[0] * a.act_stride + (size_t)g0 * 64, sm.H, HS);
+            tile_rows_async(a.features, g0, a.P, FD * L, sm.F, FS);
+            fetch_after(0, g0);
+            pipe.release();
+            __syncthreads();
+        } else {
         // ---- features of the tile (saved by the forward), hidden recomputed -------
         tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
         __syncthreads();
@@ -767,6 +834,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
+        }
 
         // ---- per-Gaussian activation backward -> small deltas in G[g][0..10] ----
         //  G: [0..2] d(dx) , [3..5] d(ds), [6..9] d(dr), [10] d(do)
@@ -786,19 +854,23 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
 
         // ---- pos head ------------------------------------------------------------
         if (n.pos.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.pos.b1, sm.A, HS);
+            float* Ab = SAVED ? abuf[1] : sm.A;
+            if (SAVED) fetch_after(1, g0);
+            else tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.pos.b1, sm.A, HS);
             if (tid < DT * 4) sm.Dout[tid] = sm.G[(tid >> 2) * 16 + (tid & 3)] * ((tid & 3) < 3 ? 1.f : 0.f);
             __syncthreads();
-            small_head_backward(sm.Dout, 3, sm.A, HS, n.pos.w2, part + a.off.pos[2], part + a.off.pos[3], sm.D1, HS);
+            small_head_backward(sm.Dout, 3, Ab, HS, n.pos.w2, part + a.off.pos[2], part + a.off.pos[3], sm.D1, HS);
             dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.pos[0], part + a.off.pos[1]);
             tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
         }
         // ---- scales head: scales_act = exp(scales + ds) ---------------------------
         {
             const bool on = n.scl.w1 != nullptr;
+            float* Ab = SAVED ? abuf[2] : sm.A;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.scl.b1, sm.A, HS);
-                tile_small_out(sm.A, HS, n.scl.w2, n.scl.b2, 3, sm.G, 16, 11);     // ds -> G[11..13]
+                if (SAVED) fetch_after(2, g0);
+                else tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.scl.b1, sm.A, HS);
+                tile_small_out(Ab, HS, n.scl.w2, n.scl.b2, 3, sm.G, 16, 11);     // ds -> G[11..13]
                 __syncthreads();
             }
             if (tid < DT * 4) {
@@ -813,7 +885,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
             }
             __syncthreads();
             if (on) {
-                small_head_backward(sm.Dout, 3, sm.A, HS, n.scl.w2, part + a.off.scl[2], part + a.off.scl[3], sm.D1, HS);
+                small_head_backward(sm.Dout, 3, Ab, HS, n.scl.w2, part + a.off.scl[2], part + a.off.scl[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.scl[0], part + a.off.scl[1]);
                 tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
@@ -821,9 +893,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         // ---- rotation head: rot_act = normalize(rot + dr) --------------------------
         {
             const bool on = n.rot.w1 != nullptr;
+            float* Ab = SAVED ? abuf[3] : sm.A;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.rot.b1, sm.A, HS);
-                tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.G, 16, 11);     // dr -> G[11..14]
+                if (SAVED) fetch_after(3, g0);
+                else tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.rot.b1, sm.A, HS);
+                tile_small_out(Ab, HS, n.rot.w2, n.rot.b2, 4, sm.G, 16, 11);     // dr -> G[11..14]
                 __syncthreads();
             }
             if (tid < DT) {
@@ -856,7 +930,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
             }
             __syncthreads();
             if (on) {
-                small_head_backward(sm.Dout, 4, sm.A, HS, n.rot.w2, part + a.off.rot[2], part + a.off.rot[3], sm.D1, HS);
+                small_head_backward(sm.Dout, 4, Ab, HS, n.rot.w2, part + a.off.rot[2], part + a.off.rot[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.rot[0], part + a.off.rot[1]);
                 tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
@@ -864,9 +938,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         // ---- opacity head: opacity_act = sigmoid(opacity + do) ---------------------
         {
             const bool on = n.opa.w1 != nullptr;
+            float* Ab = SAVED ? abuf[4] : sm.A;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.opa.b1, sm.A, HS);
-                tile_small_out(sm.A, HS, n.opa.w2, n.opa.b2, 1, sm.G, 16, 11);     // do -> G[11]
+                if (SAVED) fetch_after(4, g0);
+                else tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.opa.b1, sm.A, HS);
+                tile_small_out(Ab, HS, n.opa.w2, n.opa.b2, 1, sm.G, 16, 11);     // do -> G[11]
                 __syncthreads();
             }
             if (tid < DT * 4) {
@@ -882,7 +958,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
             }
             __syncthreads();
             if (on) {
-                small_head_backward(sm.Dout, 1, sm.A, HS, n.opa.w2, part + a.off.opa[2], part + a.off.opa[3], sm.D1, HS);
+                small_head_backward(sm.Dout, 1, Ab, HS, n.opa.w2, part + a.off.opa[2], part + a.off.opa[3], sm.D1, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.opa[0], part + a.off.opa[1]);
                 tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
@@ -903,9 +979,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                     pre_gd[i] = (a.g_dshs && idx < lim) ? __ldg(a.g_dshs + idx) : 0.f;
                 }
             }
+            float* Ab = SAVED ? abuf[5] : sm.A;
             if (on) {
-                tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
-                tile_linear<64, 48, false, false>(sm.A, HS, pipe, n.shs.b2, sm.Dout, 52);   // dshs
+                if (SAVED) fetch_after(5, g0);
+                else tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
+                tile_linear<64, 48, false, false>(Ab, HS, pipe, n.shs.b2, sm.Dout, 52);   // dshs
             } else {
                 for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dout[i] = 0.f;
                 __syncthreads();
@@ -1001,24 +1079,32 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
             }
             __syncthreads();
             if (on) {
-                dw_accum<48, 64, false>(sm.Dout, 52, sm.A, HS, part + a.off.shs[2], part + a.off.shs[3]);
-                tile_linear_T<64, 48, TL_ASSIGN_MASK>(sm.Dout, 52, pipe, sm.D1, HS, sm.A, HS);
+                dw_accum<48, 64, false>(sm.Dout, 52, Ab, HS, part + a.off.shs[2], part + a.off.shs[3]);
+                tile_linear_T<64, 48, TL_ASSIGN_MASK>(sm.Dout, 52, pipe, sm.D1, HS, Ab, HS);
                 dw_accum<64, 64, true>(sm.D1, HS, sm.H, HS, part + a.off.shs[0], part + a.off.shs[1]);
                 tile_linear_T<64, 64, TL_ACCUM_MASK>(sm.D1, HS, pipe, sm.DH, HS, sm.H, HS);
             }
         }
         // ---- dino head ------------------------------------------------------------------
         if (n.w_d0) {
-            tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
-            tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
+            float* Ad = SAVED ? abuf[6] : sm.A;
+            float* Bd = SAVED ? abuf[7] : sm.B;
+            if (SAVED) {      // d0's layer arrived during the previous head; d2's goes where that head's tile was
+                S3G_FETCH_ACT(7);
+                pipe.release();
+                __syncthreads();
+            } else {
+                tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
+                tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
+            }
             if (tid < DT * 4) {
                 const int g = tid >> 2, c = tid & 3, gi = g0 + g;
                 sm.Dout[tid] = (c < 3 && gi < a.P) ? ldz(a.g_feat, (size_t)gi * 3 + c) : 0.f;
             }
             __syncthreads();
-            small_head_backward(sm.Dout, 3, sm.B, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS);
-            dw_accum<64, 64, false>(sm.D2, HS, sm.A, HS, part + a.off.d2w, part + a.off.d2b);
-            tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, pipe, sm.D1, HS, sm.A, HS);
+            small_head_backward(sm.Dout, 3, Bd, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS);
+            dw_accum<64, 64, false>(sm.D2, HS, Ad, HS, part + a.off.d2w, part + a.off.d2b);
+            tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, pipe, sm.D1, HS, Ad, HS);
             dw_accum<64, 64, false>(sm.D1, HS, sm.H, HS, part + a.off.d0w, part + a.off.d0b);
             tile_linear_T<64, 64, TL_ACCUM>(sm.D1, HS, pipe, sm.DH, HS, nullptr, 0);
         }
@@ -1040,6 +1126,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
     }
 }
 
+#undef S3G_FETCH_ACT
+
 // ---- plane-gradient scatter + d(xyz) through the bilinear weights --------------------
 // One warp per Gaussian, lane = channel: every tap is one 128-byte-wide RED.
 struct ScatterArgs {
@@ -1050,6 +1138,11 @@ struct ScatterArgs {
     const float* dfeatures;               // [P][32L]
     float* gplanes[S3G_MAX_LEVELS][6];
     float* d_xyz;                          // [P,3], += grid path
+    // Every Gaussian of a call has the same time coordinate, so on the three planes with a time axis (k = 2, 4, 5)
+    // all of them hit the same two texel rows with the same two row weights.  Their gradients are accumulated per
+    // spatial texel in tacc[level][axis] ([reso][32], zeroed by the host) - two REDs instead of four - and
+    // hexplane_time_rows_kernel spreads the sums over the two rows afterwards: 72 instead of 96 REDs per Gaussian.
+    float* tacc[S3G_MAX_LEVELS][3];
 };
 // (capping the registers at 80 for a third resident block per SM was measured: 26.5 vs 25.7 ms for the whole deform
 // fwd+bwd at 2 M - the kernel is bound by L2 atomic / load throughput, not by occupancy; profiles/r02h_scatter_ab.log)
@@ -1123,10 +1216,16 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
                     float wx0[4], wx1[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { wx0[c] = X.omf * ds[c]; wx1[c] = X.f * ds[c]; }
+                    if (cb == 3) {      // time plane: per-texel sums, the row weights are applied once afterwards
+                        float* tp = a.tacc[l][ca] + q4;
+                        red4(tp + (uint32_t)X.i0 * FD, wx0[0], wx0[1], wx0[2], wx0[3]);
+                        red4(tp + (uint32_t)X.i1 * FD, wx1[0], wx1[1], wx1[2], wx1[3]);
+                    } else {
                     red4(gp + o00[k], wx0[0] * Y.omf, wx0[1] * Y.omf, wx0[2] * Y.omf, wx0[3] * Y.omf);
                     red4(gp + o01[k], wx1[0] * Y.omf, wx1[1] * Y.omf, wx1[2] * Y.omf, wx1[3] * Y.omf);
                     red4(gp + o10[k], wx0[0] * Y.f, wx0[1] * Y.f, wx0[2] * Y.f, wx0[3] * Y.f);
                     red4(gp + o11[k], wx1[0] * Y.f, wx1[1] * Y.f, wx1[2] * Y.f, wx1[3] * Y.f);
+                    }
                 }
                 // d(sample)/d(ix), d(sample)/d(iy)
                 const float vv[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
@@ -1150,6 +1249,28 @@ __global__ void __launch_bounds__(256, 2) hexplane_scatter_kernel(ScatterArgs a)
             a.d_xyz[(size_t)gi * 3 + q] += d * n.inv_span2[q];
         }
     }
+}
+
+// gplane[l][k][t0][ix] += (1 - f_t) * tacc[l][axis][ix],  gplane[l][k][t1][ix] += f_t * tacc[l][axis][ix]  for the three
+// planes with a time axis; runs after the scatter kernel on the same stream (no other writer of these planes then).
+struct TimeRowsArgs {
+    DNet net;
+    float time;
+    float* gplanes[S3G_MAX_LEVELS][6];
+    const float* tacc[S3G_MAX_LEVELS][3];
+};
+static __global__ void __launch_bounds__(256) hexplane_time_rows_kernel(TimeRowsArgs a) {
+    const int l = blockIdx.z, axis = blockIdx.y;
+    const int k = axis == 0 ? 2 : (axis == 1 ? 4 : 5);
+    const int W = a.net.reso[l][axis];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W * FD) return;
+    const AxisTap T = axis_tap(a.time, a.net.reso[l][3]);
+    const float v = a.tacc[l][axis][e];
+    float* gp = a.gplanes[l][k];
+    // a border-clamped second row has weight exactly 0 and aliases the first: adding 0.0 leaves it unchanged
+    gp[(size_t)T.i0 * W * FD + e] += T.omf * v;
+    gp[(size_t)T.i1 * W * FD + e] += T.f * v;
 }
 
 // sum the per-CTA partial Linear gradients: one thread per gradient element

@@ -52,24 +52,45 @@ inline int to_dnet(const s3g_deform_net* n, DNet& d) {
         return fail(S3G_ERR_ARG, "deform: incomplete dino head");
     return S3G_OK;
 }
-// weight matrices in the order one tile consumes them (see WPipe)
-inline void build_wseq(const DNet& d, bool backward, WSeq& q) {
+// weight matrices in the order one tile consumes them (see WPipe).  `saved`: the backward reads the hidden
+// activations the forward stored instead of recomputing them, so only the push-back products (and the 48-wide SH
+// output layer, whose result is not stored) remain.
+inline void build_wseq(const DNet& d, bool backward, WSeq& q, bool saved = false) {
     q.count = 0;
     auto add = [&](const float* W, int N, int K) { q.W[q.count] = W; q.N[q.count] = (short)N; q.K[q.count] = (short)K; ++q.count; };
     const int KF = FD * d.L;
-    add(d.w_feat, 64, KF);
+    if (!saved) add(d.w_feat, 64, KF);
     const Head2* small[4] = {&d.pos, &d.scl, &d.rot, &d.opa};
     for (const Head2* h : small)
-        if (h->w1) { add(h->w1, 64, 64); if (backward) add(h->w1, 64, 64); }
+        if (h->w1) { if (!saved) add(h->w1, 64, 64); if (backward) add(h->w1, 64, 64); }
     if (d.shs.w1) {
-        add(d.shs.w1, 64, 64); add(d.shs.w2, 48, 64);
+        if (!saved) add(d.shs.w1, 64, 64);
+        add(d.shs.w2, 48, 64);
         if (backward) { add(d.shs.w2, 48, 64); add(d.shs.w1, 64, 64); }
     }
     if (d.w_d0) {
-        add(d.w_d0, 64, 64); add(d.w_d2, 64, 64);
+        if (!saved) { add(d.w_d0, 64, 64); add(d.w_d2, 64, 64); }
         if (backward) { add(d.w_d2, 64, 64); add(d.w_d0, 64, 64); }
     }
     if (backward) add(d.w_feat, 64, KF);
+}
+
+// Hidden activations the tcgen05 forward can keep for the backward: [slot][P][64] floats, one slot per enabled
+// kind in this order.  Returns the slot count and fills slot[kind] (-1 = absent).  0 when the forward that
+// runs for this net (L > 4: the mma.sync kernel) does not store them.
+enum { AK_H = 0, AK_POS, AK_SCL, AK_ROT, AK_OPA, AK_SHS, AK_D0, AK_D2, AK_COUNT };
+inline int act_slots(const DNet& d, int (&slot)[AK_COUNT]) {
+    for (int i = 0; i < AK_COUNT; ++i) slot[i] = -1;
+    if (d.L > 4) return 0;
+    int n = 0;
+    slot[AK_H] = n++;
+    if (d.pos.w1) slot[AK_POS] = n++;
+    if (d.scl.w1) slot[AK_SCL] = n++;
+    if (d.rot.w1) slot[AK_ROT] = n++;
+    if (d.opa.w1) slot[AK_OPA] = n++;
+    if (d.shs.w1) slot[AK_SHS] = n++;
+    if (d.w_d0) { slot[AK_D0] = n++; slot[AK_D2] = n++; }
+    return n;
 }
 
 }  // namespace s3g

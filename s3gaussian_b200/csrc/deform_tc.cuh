@@ -65,6 +65,13 @@ struct DeformTcArgs {
     const float* features;     // [P][32L]
     const float* wprep;        // prepared weights (TcTable offsets)
     TcTable tab;
+    // Hidden activations kept for the backward (or NULL): [slot][tile][128 x 64 operand tile], i.e. every stored tile
+    // is the shared-memory image of the K-major operand it was for the next layer, written by ONE bulk async copy
+    // (cp.async.bulk shared -> global) issued next to that layer's MMAs - no per-thread stores.  The hi operand
+    // holds the fp32 value itself (the tensor core ignores the low mantissa bits), so the copy is exact.
+    float* acts;
+    int act_slot[8];           // slot of H, pos, scl, rot, opa, shs, d0, d2 (deform_host.cuh: AK_*), -1 = absent
+    size_t act_stride;         // floats per slot = ceil(P / 128) * 128 * 64
 };
 
 struct TcCtx {
@@ -86,14 +93,20 @@ __device__ __forceinline__ void tc_fetch_weights(TcCtx& c, int layer) {   // thr
 // All 128 threads.  The operand for `layer` has just been written to op_hi/op_lo by its owners.
 // Runs the layer into TMEM columns [col, col+npad) and returns when the accumulators are readable;
 // meanwhile the weights of `next_layer` (or -1) start streaming into the weight buffer.
-__device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, int next_layer) {
+// `keep` (or NULL): global destination of this layer's hi operand tile (128 x K floats), see DeformTcArgs::acts.
+__device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, int next_layer, float* keep = nullptr) {
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) {
+        const int K = c.tab->k[layer], NP = c.tab->npad[layer];
+        if (keep) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(keep), "r"(umma::smem_u32(c.op_hi)), "r"((uint32_t)(TCM * K) * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         umma::mbar_wait(c.w_bar, c.wph);
         umma::fence_after_sync();
-        const int K = c.tab->k[layer], NP = c.tab->npad[layer];
         const uint32_t idesc = umma::make_idesc_tf32(TCM, NP);
         const uint32_t sbo = (uint32_t)(K / 4) * 128u;
         const uint32_t a_hi = umma::smem_u32(c.op_hi), a_lo = umma::smem_u32(c.op_lo);
@@ -106,6 +119,9 @@ __device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, 
             umma::mma_tf32(c.tmem + col, dah, dbl, idesc, true);
             umma::mma_tf32(c.tmem + col, dah, dbh, idesc, true);
         }
+        // the operand buffer is rewritten once mma_bar flips: the copy must have read it by then (it runs while the
+        // MMAs do, so this wait is normally already satisfied)
+        if (keep) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         umma::commit(c.mma_bar);
     }
     umma::mbar_wait(c.mma_bar, c.mph);
@@ -146,13 +162,13 @@ __device__ __forceinline__ void tc_load_row64(const TcCtx& c, uint32_t col, cons
 // two-layer head on relu(h) (or raw h): returns the first 32 output columns (+bias) of the last layer
 template <bool RELU_IN>
 __device__ __forceinline__ void tc_head2(TcCtx& c, int row, const float (&h)[64], int l1, int l2, const float* sB1, int next,
-                                         float (&out)[32]) {
+                                         float (&out)[32], float* keep_h, float* keep_a) {
     tc_store_row64<RELU_IN>(c, row, h);
-    tc_run_layer(c, l1, 64, l2);
+    tc_run_layer(c, l1, 64, l2, keep_h);
     float a[64];
     tc_load_row64(c, 64, sB1, a);
     tc_store_row64<true>(c, row, a);
-    tc_run_layer(c, l2, 128, next);
+    tc_run_layer(c, l2, 128, next, keep_a);
     const uint32_t lane_base = (uint32_t)((threadIdx.x >> 5) * 32) << 16;
     umma::tmem_ld32(c.tmem + lane_base + 128, out);
 }
@@ -224,39 +240,49 @@ __global__ void __launch_bounds__(TCM, 1) deform_forward_tc_kernel(const __grid_
         tc_run_layer(c, TL_FEAT, 0, first_after_feat);
         float h[64];
         tc_load_row64(c, 0, s_bias + TL_FEAT * 64, h);
+        // where this tile's kept activations go; h is kept raw when the dino head (the one consumer of raw h) is on,
+        // else as the relu(h) operand of the first enabled head (mask and products of the backward only need that)
+        auto keep = [&](int kind) -> float* {
+            return (a.acts && a.act_slot[kind] >= 0) ? a.acts + (size_t)a.act_slot[kind] * a.act_stride + (size_t)tile * (TCM * 64) : nullptr;
+        };
+        float* keep_h = on_d ? nullptr : keep(0);      // handed to the first relu head that runs, then cleared
 
         float dxv[3] = {0.f, 0.f, 0.f}, dsv[3] = {0.f, 0.f, 0.f}, drv[4] = {0.f, 0.f, 0.f, 0.f}, dov = 0.f, featv[3] = {0.f, 0.f, 0.f};
         float o32[32];
         if (on_pos) {
-            tc_head2<true>(c, tid, h, TL_POS1, TL_POS2, s_bias + TL_POS1 * 64, after_pos, o32);
+            tc_head2<true>(c, tid, h, TL_POS1, TL_POS2, s_bias + TL_POS1 * 64, after_pos, o32, keep_h, keep(1));
+            keep_h = nullptr;
 #pragma unroll
             for (int i = 0; i < 3; ++i) dxv[i] = o32[i] + s_bias[TL_POS2 * 64 + i];
         }
         if (on_scl) {
-            tc_head2<true>(c, tid, h, TL_SCL1, TL_SCL2, s_bias + TL_SCL1 * 64, after_scl, o32);
+            tc_head2<true>(c, tid, h, TL_SCL1, TL_SCL2, s_bias + TL_SCL1 * 64, after_scl, o32, keep_h, keep(2));
+            keep_h = nullptr;
 #pragma unroll
             for (int i = 0; i < 3; ++i) dsv[i] = o32[i] + s_bias[TL_SCL2 * 64 + i];
         }
         if (on_rot) {
-            tc_head2<true>(c, tid, h, TL_ROT1, TL_ROT2, s_bias + TL_ROT1 * 64, after_rot, o32);
+            tc_head2<true>(c, tid, h, TL_ROT1, TL_ROT2, s_bias + TL_ROT1 * 64, after_rot, o32, keep_h, keep(3));
+            keep_h = nullptr;
 #pragma unroll
             for (int i = 0; i < 4; ++i) drv[i] = o32[i] + s_bias[TL_ROT2 * 64 + i];
         }
         if (on_opa) {
-            tc_head2<true>(c, tid, h, TL_OPA1, TL_OPA2, s_bias + TL_OPA1 * 64, after_opa, o32);
+            tc_head2<true>(c, tid, h, TL_OPA1, TL_OPA2, s_bias + TL_OPA1 * 64, after_opa, o32, keep_h, keep(4));
+            keep_h = nullptr;
             dov = o32[0] + s_bias[TL_OPA2 * 64];
         }
         // ---- dino head (no leading ReLU) -----------------------------------------------------------
         if (on_d) {
             tc_store_row64<false>(c, tid, h);
-            tc_run_layer(c, TL_D0, 64, TL_D2);
+            tc_run_layer(c, TL_D0, 64, TL_D2, keep(0));
             float av[64];
             tc_load_row64(c, 64, s_bias + TL_D0 * 64, av);
             tc_store_row64<true>(c, tid, av);
-            tc_run_layer(c, TL_D2, 128, TL_D4);
+            tc_run_layer(c, TL_D2, 128, TL_D4, keep(6));
             tc_load_row64(c, 128, s_bias + TL_D2 * 64, av);
             tc_store_row64<true>(c, tid, av);
-            tc_run_layer(c, TL_D4, 192, after_d);
+            tc_run_layer(c, TL_D4, 192, after_d, keep(7));
             umma::tmem_ld32(c.tmem + lane_base + 192, o32);
 #pragma unroll
             for (int i = 0; i < 3; ++i) featv[i] = o32[i] + s_bias[TL_D4 * 64 + i];
@@ -281,11 +307,12 @@ __global__ void __launch_bounds__(TCM, 1) deform_forward_tc_kernel(const __grid_
         }
         if (on_shs) {
             tc_store_row64<true>(c, tid, h);
-            tc_run_layer(c, TL_SHS1, 64, TL_SHS2);
+            tc_run_layer(c, TL_SHS1, 64, TL_SHS2, keep_h);
+            keep_h = nullptr;
             float av[64];
             tc_load_row64(c, 64, s_bias + TL_SHS1 * 64, av);
             tc_store_row64<true>(c, tid, av);
-            tc_run_layer(c, TL_SHS2, 128, after_shs);
+            tc_run_layer(c, TL_SHS2, 128, after_shs, keep(5));
         }
         {   // dshs (48 columns at TMEM col 128) in two halves: out, shs + dshs, colour accumulation
             float* dshs_row = a.o_dshs ? a.o_dshs + (size_t)(valid ? gi : 0) * 48 : nullptr;

@@ -71,6 +71,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+# True: the forward keeps the decoder's hidden activations for the backward (s3g_deform_forward_save /
+# s3g_deform_backward_saved, 256 B per Gaussian and hidden layer).  False: the backward recomputes them from the
+# sampled features (s3g_deform_backward), which trades ~30 % more backward time for that memory.
+SAVE_ACTIVATIONS = True
+
+
 class HexPlaneField(nn.Module):
     """Parameter container with the reference's names (scene/hexplane.py:109-158)."""
 
@@ -313,12 +319,17 @@ class _DeformFront(torch.autograd.Function):
         features = e(P, 32 * len(module.deformation_net.grid.grids))     # sampler -> decoder hand-over, kept for backward
         campos_ = campos.detach().to(device=dev, dtype=torch.float32).contiguous()
         fws = torch.empty(int(lib.s3g_deform_forward_workspace_bytes(C.byref(cnet))), dtype=torch.uint8, device=dev)
+        # when a backward will follow, the decoder's hidden activations are kept (what autograd keeps for the reference's
+        # nn.Sequential heads) so that the backward kernel does not recompute them (opaque buffer, 256 B per Gaussian
+        # and hidden layer)
+        nbytes = int(lib.s3g_deform_saved_bytes(C.byref(cnet), P)) if (SAVE_ACTIVATIONS and any(ctx.needs_input_grad)) else 0
+        acts = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
         with torch.cuda.device(dev):
-            _lib.check(lib.s3g_deform_forward(C.byref(cnet), P, _p(xyz_), _p(sc_), _p(ro_), _p(op_), _p(shs_),
-                                              float(time), _p(campos_), int(sh_degree), _p(means), _p(sc_o),
-                                              _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat), _p(features), _p(fws),
-                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                       "s3g_deform_forward")
+            _lib.check(lib.s3g_deform_forward_save(C.byref(cnet), P, _p(xyz_), _p(sc_), _p(ro_), _p(op_), _p(shs_),
+                                                   float(time), _p(campos_), int(sh_degree), _p(means), _p(sc_o),
+                                                   _p(ro_o), _p(op_o), _p(colors), _p(dx), _p(dshs), _p(feat), _p(features),
+                                                   _p(acts), _p(fws), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "s3g_deform_forward_save")
         if raw_outputs:
             # forward_dynamic returns the un-activated values; with the default flags those are the inputs
             a = module.args
@@ -326,14 +337,18 @@ class _DeformFront(torch.autograd.Function):
                 raise NotImplementedError("forward_dynamic with scale/rotation/opacity heads: use render_front()")
             sc_o, ro_o, op_o = sc_.clone(), ro_.clone(), op_.clone()
         ctx.module, ctx.time, ctx.sh_degree, ctx.raw, ctx.names = module, float(time), int(sh_degree), raw_outputs, names
-        ctx.save_for_backward(xyz_, sc_, ro_, op_, shs_, campos_, features, *[p.detach() for p in params])
+        ctx.has_acts = acts is not None
+        ctx.save_for_backward(xyz_, sc_, ro_, op_, shs_, campos_, features, acts if acts is not None else torch.empty(0, dtype=torch.uint8, device=dev),
+                              *[p.detach() for p in params])
         return means, sc_o, ro_o, op_o, colors, dx, dshs, feat
 
     @staticmethod
     def backward(ctx, g_means, g_sc, g_ro, g_op, g_col, g_dx, g_dshs, g_feat):
         lib = _lib.load()
         module = ctx.module
-        xyz, sc, ro, op, shs, campos, features, *params = ctx.saved_tensors
+        xyz, sc, ro, op, shs, campos, features, acts, *params = ctx.saved_tensors
+        if not ctx.has_acts:
+            acts = None
         dev = xyz.device
         P = xyz.shape[0]
         byname = dict(zip(ctx.names, params))
@@ -354,12 +369,12 @@ class _DeformFront(torch.autograd.Function):
         module._fill(cnet, byname, grads=(cg, pgrads))
         ws = torch.empty(int(lib.s3g_deform_workspace_bytes(C.byref(cnet), P)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.s3g_deform_backward(C.byref(cnet), P, _p(xyz), _p(sc), _p(ro), _p(op), _p(shs), ctx.time,
-                                               _p(campos), ctx.sh_degree, _p(features), _p(g_means), _p(g_sc), _p(g_ro), _p(g_op),
-                                               _p(g_col), _p(g_dx), _p(g_dshs), _p(g_feat), _p(d_xyz), _p(d_sc),
-                                               _p(d_ro), _p(d_op), _p(d_shs), C.byref(cg), _p(ws),
-                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                       "s3g_deform_backward")
+            _lib.check(lib.s3g_deform_backward_saved(C.byref(cnet), P, _p(xyz), _p(sc), _p(ro), _p(op), _p(shs), ctx.time,
+                                                     _p(campos), ctx.sh_degree, _p(features), _p(acts), _p(g_means), _p(g_sc),
+                                                     _p(g_ro), _p(g_op), _p(g_col), _p(g_dx), _p(g_dshs), _p(g_feat), _p(d_xyz),
+                                                     _p(d_sc), _p(d_ro), _p(d_op), _p(d_shs), C.byref(cg), _p(ws),
+                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "s3g_deform_backward_saved")
         if ctx.raw:
             if raw_sc is not None:
                 d_sc = d_sc + raw_sc

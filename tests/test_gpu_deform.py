@@ -29,8 +29,13 @@ def build_net(z, st, flags):
     return net.to(DEV)
 
 
+@pytest.mark.parametrize("saved", [True, False], ids=["saved_activations", "recompute"])
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[7:-4] for p in GOLD])
-def test_fused_deform_matches_reference_golden(path, built_lib):
+def test_fused_deform_matches_reference_golden(path, saved, built_lib, monkeypatch):
+    """both backward variants against the reference's golden gradients: hidden activations kept by the tcgen05
+    forward (s3g_deform_forward_save / s3g_deform_backward_saved) and recomputed in the backward kernel"""
+    from s3gaussian_b200 import deformation
+    monkeypatch.setattr(deformation, "SAVE_ACTIVATIONS", saved)
     z, st, flags = load_deform_case(path)
     net = build_net(z, st, flags)
     T = lambda k: torch.from_numpy(z[k]).to(DEV).requires_grad_(True)

@@ -74,16 +74,25 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// the three products of NT independent accumulators, interleaved so that consecutive HMMAs never depend on each other
+// The three products of NT output tiles.  The two small cross terms accumulate in `ds`, the hi*hi term in `d` (summed by
+// the caller at the end): 2 NT independent HMMA chains per warp instead of NT, and dependent HMMAs are 2 NT
+// instructions apart - the tensor pipe's result latency was 16 % of the backward kernel's stall samples ("wait").
 template <int NT>
-__device__ __forceinline__ void mma3_multi(float (&d)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+__device__ __forceinline__ void mma3_multi(float (&d)[NT][4], float (&ds)[NT][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                            const uint32_t (&bh)[NT][2], const uint32_t (&bl)[NT][2]) {
 #pragma unroll
-    for (int j = 0; j < NT; ++j) mma_tf32(d[j], al, bh[j]);   // small terms first
-#pragma unroll
-    for (int j = 0; j < NT; ++j) mma_tf32(d[j], ah, bl[j]);
+    for (int j = 0; j < NT; ++j) mma_tf32(ds[j], al, bh[j]);
 #pragma unroll
     for (int j = 0; j < NT; ++j) mma_tf32(d[j], ah, bh[j]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_tf32(ds[j], ah, bl[j]);
+}
+template <int NT>
+__device__ __forceinline__ void mma3_fold(float (&d)[NT][4], const float (&ds)[NT][4]) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[j][i] += ds[j][i];
 }
 
 // Stage a PyTorch-layout weight [N][K] (row n contiguous) into smem rows of stride K+4.
@@ -113,7 +122,9 @@ __device__ __forceinline__ void cp_async16_w(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 struct WPipe {
-    float* buf[2];
+    // NB: no dynamically indexed member arrays - `buf[cur]` put the whole struct into local memory, and the LDLs at the
+    // head of every product were 19 % of the backward kernel's stall samples (profiles/r02u)
+    float *b0, *b1;
     int cur, wi, count;
     const WSeq* seq;     // shared-memory copy (a dynamically indexed kernel parameter is a long-scoreboard load)
     // descriptor of layer wi + 1, read one product ahead of its use so that acquire() never waits on it
@@ -136,13 +147,13 @@ struct WPipe {
         nNew = nW != seq->W[wi];
     }
     // kernel prologue: copies the sequence to shared memory, fetches layer 0 and ends with a barrier
-    __device__ __forceinline__ void start(const WSeq& src, WSeq* s_seq, float* b0, float* b1) {
+    __device__ __forceinline__ void start(const WSeq& src, WSeq* s_seq, float* b0_, float* b1_) {
         for (int i = threadIdx.x; i < (int)(sizeof(WSeq) / 4); i += DTHREADS)
             reinterpret_cast<uint32_t*>(s_seq)[i] = reinterpret_cast<const uint32_t*>(&src)[i];
         __syncthreads();
-        seq = s_seq; buf[0] = b0; buf[1] = b1;
+        seq = s_seq; b0 = b0_; b1 = b1_;
         cur = 0; wi = 0; count = s_seq->count;
-        prefetch(s_seq->W[0], s_seq->K[0], s_seq->N[0], buf[0]);
+        prefetch(s_seq->W[0], s_seq->K[0], s_seq->N[0], b0);
         load_next();
         release();
         __syncthreads();
@@ -151,9 +162,9 @@ struct WPipe {
     // visible); the next layer's start flowing into the other buffer, which nobody reads any more since that
     // same barrier.  No barrier of its own: one per product instead of two.
     __device__ __forceinline__ float* acquire() {
-        float* mine = buf[cur];
+        float* mine = cur ? b1 : b0;
         if (nNew) {
-            prefetch(nW, nK, nN, buf[cur ^ 1]);
+            prefetch(nW, nK, nN, cur ? b0 : b1);
             cur ^= 1;
         }
         wi = (wi + 1 == count) ? 0 : wi + 1;
@@ -179,9 +190,11 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
     const int r0 = (warp & 3) * 16;
     const int c0 = (warp >> 2) * 16;
     const bool active = c0 < N;
-    float acc[NTW][4];
+    float acc[NTW][4], accs[NTW][4];
 #pragma unroll
-    for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < NTW; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = accs[j][i] = 0.f;
     const float* rowA = sIn + (r0 + g) * inStride + t;
     const float* rowB = sIn + (r0 + g + 8) * inStride + t;
     float bias[NTW][2];                  // fetched before the k loop so the epilogue does not wait on L2
@@ -207,8 +220,9 @@ __device__ __forceinline__ void tile_linear(const float* sIn, int inStride, WPip
             split_tf32(wr[0], bh[j][0], bl[j][0]);
             split_tf32(wr[4], bh[j][1], bl[j][1]);
         }
-        mma3_multi<NTW>(acc, ah, al, bh, bl);
+        mma3_multi<NTW>(acc, accs, ah, al, bh, bl);
     }
+    mma3_fold<NTW>(acc, accs);
 #pragma unroll
     for (int j = 0; j < NTW; ++j) {
         if (!active) break;
@@ -561,9 +575,11 @@ __device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r0 = (warp & 3) * 16;
     const int c0 = (warp >> 2) * (K / 4);
-    float acc[NTW][4];
+    float acc[NTW][4], accs[NTW][4];
 #pragma unroll
-    for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < NTW; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = accs[j][i] = 0.f;
     // The contraction index of an MMA can be permuted freely as long as A and B agree: fragment slots (t, t+4)
     // take the physical indices (2t, 2t+1).  The weight reads W[n0+2t(+1)][c+g] then fall on banks 8t+g (+4)
     // (row stride == 4 mod 32): conflict-free, where the natural slots gave 4t+g, two-way conflicts.
@@ -583,8 +599,9 @@ __device__ __forceinline__ void tile_linear_T(const float* sIn, int inStride, WP
             split_tf32(wr[0], bh[j][0], bl[j][0]);
             split_tf32(wr[WS], bh[j][1], bl[j][1]);
         }
-        mma3_multi<NTW>(acc, ah, al, bh, bl);
+        mma3_multi<NTW>(acc, accs, ah, al, bh, bl);
     }
+    mma3_fold<NTW>(acc, accs);
 #pragma unroll
     for (int j = 0; j < NTW; ++j) {
         const int col = c0 + 8 * j + 2 * t;
@@ -617,9 +634,11 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
     constexpr int ITEMS = (M / 16) * (TN / NT);
     for (int item = warp; item < ITEMS; item += DTHREADS / 32) {
         const int m0 = (item / (TN / NT)) * 16, n0 = (item % (TN / NT)) * (8 * NT);
-        float acc[NT][4];
+        float acc[NT][4], accs[NT][4];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = accs[j][i] = 0.f;
 #pragma unroll 2
         for (int k0 = 0; k0 < DT; k0 += 8) {
             // A[m][k] = delta[k][m]; contraction slots (t, t+4) -> rows (2t, 2t+1) of the tile: banks 8t+g for
@@ -638,8 +657,9 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
                 split_tf32(b[0], bh[j][0], bl[j][0]);
                 split_tf32(b[1], bh[j][1], bl[j][1]);
             }
-            mma3_multi<NT>(acc, ah, al, bh, bl);
+            mma3_multi<NT>(acc, accs, ah, al, bh, bl);
         }
+        mma3_fold<NT>(acc, accs);
         // fire-and-forget REDs on the CTA-private partial buffer: a load-add-store would expose
         // one L2 round trip per output tile (measured: 14 ms of a 55 ms step)
 #pragma unroll
@@ -662,7 +682,8 @@ __device__ __forceinline__ void dw_accum(const float* sDelta, int dStride, const
 //   D[g][j] = (sum_o dout[g][o] * W2[o][j]) * [act[g][j] > 0]
 __device__ __forceinline__ void small_head_backward(const float* sDout, int k, const float* sAct, int aStride,
                                                     const float* __restrict__ W2, float* __restrict__ gW2,
-                                                    float* __restrict__ gb2, float* sD, int dStride) {
+                                                    float* __restrict__ gb2, float* sD, int dStride,
+                                                    bool wait_async = false) {
     const int tid = threadIdx.x;
     {   // weight grads: thread -> (o, j)
         const int o = tid >> 6, j = tid & 63;
@@ -683,6 +704,7 @@ __device__ __forceinline__ void small_head_backward(const float* sDout, int k, c
         for (int o = 0; o < k; ++o) v = fmaf(sDout[g * 4 + o], __ldg(W2 + o * HWID + j), v);
         sD[g * dStride + j] = sAct[g * aStride + j] > 0.f ? v : 0.f;
     }
+    if (wait_async) asm volatile("cp.async.wait_all;" ::: "memory");    // tiles requested before the call are visible after it
     __syncthreads();
 }
 
@@ -792,12 +814,16 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
     __syncthreads();
     // SAVED: which of the two activation buffers each stored tile lands in (consecutive enabled kinds alternate)
     const bool on_pos = n.pos.w1, on_scl = n.scl.w1, on_rot = n.rot.w1, on_opa = n.opa.w1, on_shs = n.shs.w1, on_d = n.w_d0;
+    // The dino head needs its second hidden layer first, so that one travels a head ahead and takes the next
+    // buffer in turn; the first hidden layer follows at the start of the head into the buffer the previous head used.
     float* abuf[8];
     {
         int j = 0;
-        const bool en[8] = {false, on_pos, on_scl, on_rot, on_opa, on_shs, on_d, on_d};
+        const bool en[6] = {false, on_pos, on_scl, on_rot, on_opa, on_shs};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { abuf[k] = (j & 1) ? sm.B : sm.A; if (en[k]) ++j; }
+        for (int k = 0; k < 6; ++k) { abuf[k] = (j & 1) ? sm.B : sm.A; if (en[k]) ++j; }
+        abuf[7] = (j & 1) ? sm.B : sm.A;
+        abuf[6] = (j & 1) ? sm.A : sm.B;
     }
 #define S3G_FETCH_ACT(KIND) tile_canon_async(a.acts + (size_t)a.act_slot[KIND] * a.act_stride + (size_t)g0 * 64, abuf[KIND], HS)
     // start the load of the first enabled activation kind after `kind` (a compile-time constant at every call)
@@ -807,25 +833,25 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         else if (kind < 3 && on_rot) S3G_FETCH_ACT(3);
         else if (kind < 4 && on_opa) S3G_FETCH_ACT(4);
         else if (kind < 5 && on_shs) S3G_FETCH_ACT(5);
-        else if (kind < 6 && on_d) S3G_FETCH_ACT(6);
+        else if (kind < 6 && on_d) S3G_FETCH_ACT(7);
     };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int g0 = tile * DT;
+        if (SAVED) {
+            // ---- h, the features (for the last product pair) and the first head's hidden layer: stored by the forward.
+            // The copies fly while the tile's scalars are set up; one barrier (after G below) covers all of it.
+            tile_canon_async(a.acts + (size_t)a.act_slot[0] * a.act_stride + (size_t)g0 * 64, sm.H, HS);
+            fetch_after(0, g0);
+            tile_rows_async(a.features, g0, a.P, FD * L, sm.F, FS);     // last group: only the final product pair reads it
+        }
         if (tid < DT * 3) {
             const int g = tid / 3, c = tid - 3 * g;
             sm.X[g * 4 + c] = (g0 + g < a.P) ? a.xyz[(size_t)(g0 + g) * 3 + c] : 0.f;
         }
         for (int i = tid; i < DT * HS; i += DTHREADS) sm.DH[i] = 0.f;
+        if (!SAVED) {
         __syncthreads();
-        if (SAVED) {
-            // ---- h, the features (for the last product pair) and the first head's hidden layer: stored by the forward
-            tile_canon_async(a.acts + (size_t)a.act_slot[0] * a.act_stride + (size_t)g0 * 64, sm.H, HS);
-            tile_rows_async(a.features, g0, a.P, FD * L, sm.F, FS);
-            fetch_after(0, g0);
-            pipe.release();
-            __syncthreads();
-        } else {
         // ---- features of the tile (saved by the forward), hidden recomputed -------
         tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
         __syncthreads();
@@ -848,6 +874,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                 for (int c = 0; c < 3; ++c) G[c] = ldz(a.g_means, (size_t)gi * 3 + c) + ldz(a.g_dx, (size_t)gi * 3 + c);
             }
         }
+        if (SAVED) asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the features
         __syncthreads();
         // scales / rotation / opacity need their head outputs first (when the heads are on), so
         // the forward of those heads is recomputed into S-like columns of G[11..15] lazily below.
@@ -995,33 +1022,31 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                 if (g0 + g < a.P) sm.Dout[g * 52 + j] += pre_shs[i];
             }
             __syncthreads();
-            // per Gaussian: colour clamp mask, dL/dshs_final = basis (x) g_col, dL/d(dir) -> d_xyz part (into G[11..13])
-            if (tid < DT) {
-                const int g = tid, gi = g0 + g;
-                float dxyz[3] = {0.f, 0.f, 0.f};
+            // per (Gaussian, colour channel) - four lanes per Gaussian, the fourth idles: colour clamp mask,
+            // dL/dshs_final = basis (x) g_col, dL/d(dir) -> d_xyz part (into G[11..13]).  (One thread per Gaussian left
+            // 14 of the 16 warps waiting at the next barrier for the longest scalar stretch of the tile.)
+            if (tid < DT * 4) {
+                const int g = tid >> 2, c = tid & 3, gi = g0 + g;
+                const bool live = gi < a.P;
                 float bs[16];
-                float gr[3] = {0.f, 0.f, 0.f};
+                float grc = 0.f;
                 int nb = 0;
-                if (gi < a.P) {
-                    const float vx = sm.X[g * 4 + 0] - a.campos[0], vy = sm.X[g * 4 + 1] - a.campos[1],
-                                vz = sm.X[g * 4 + 2] - a.campos[2];
-                    const float s2 = vx * vx + vy * vy + vz * vz;
+                float dd[3] = {0.f, 0.f, 0.f};      // this channel's share of dL/d(dir)
+                float vx = 0.f, vy = 0.f, vz = 0.f, s2 = 1.f;
+                float* sf = sm.Dout + g * 52;
+                if (live) {
+                    vx = sm.X[g * 4 + 0] - a.campos[0]; vy = sm.X[g * 4 + 1] - a.campos[1]; vz = sm.X[g * 4 + 2] - a.campos[2];
+                    s2 = vx * vx + vy * vy + vz * vz;
                     const float inv = 1.0f / sqrtf(s2);
                     const float x = vx * inv, y = vy * inv, z = vz * inv;
                     nb = sh_basis16(a.sh_degree, x, y, z, bs);
-                    float* sf = sm.Dout + g * 52;
-                    float ddir[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
+                    if (c < 3) {
                         float r = 0.f;
                         for (int k = 0; k < nb; ++k) r = fmaf(bs[k], sf[3 * k + c], r);
-                        gr[c] = (r + 0.5f > 0.0f) ? ldz(a.g_colors, (size_t)gi * 3 + c) : 0.f;   // clamp_min(.,0)
-                    }
-                    if (a.sh_degree > 0) {
-                        const float C1 = 0.4886025119029199f;
-                        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
+                        grc = (r + 0.5f > 0.0f) ? ldz(a.g_colors, (size_t)gi * 3 + c) : 0.f;   // clamp_min(.,0)
+                        if (a.sh_degree > 0) {
+                            const float C1 = 0.4886025119029199f;
+                            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
 #define SHF(i) sf[3 * (i) + c]
                             float dx_ = -C1 * SHF(3), dy_ = -C1 * SHF(1), dz_ = C1 * SHF(2);
                             if (a.sh_degree > 1) {
@@ -1046,22 +1071,31 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                                        -0.4570457994644658f * SHF(13) * 8.f * xz + 1.445305721320277f * SHF(14) * (xx - yy);
                             }
 #undef SHF
-                            ddir[0] += dx_ * gr[c]; ddir[1] += dy_ * gr[c]; ddir[2] += dz_ * gr[c];
+                            dd[0] = dx_ * grc; dd[1] = dy_ * grc; dd[2] = dz_ * grc;
                         }
-                        // through dir = v / |v|
-                        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
-                        const float dot = vx * ddir[0] + vy * ddir[1] + vz * ddir[2];
-                        dxyz[0] = (s2 * ddir[0] - vx * dot) * inv32;
-                        dxyz[1] = (s2 * ddir[1] - vy * dot) * inv32;
-                        dxyz[2] = (s2 * ddir[2] - vz * dot) * inv32;
                     }
                 }
-                sm.G[g * 16 + 11] = dxyz[0]; sm.G[g * 16 + 12] = dxyz[1]; sm.G[g * 16 + 13] = dxyz[2];
-                // overwrite the row with dL/dshs_final
-                float* sf = sm.Dout + g * 52;
-                for (int k = 0; k < 16; ++k) {
-                    const float b = k < nb ? bs[k] : 0.f;
-                    sf[3 * k + 0] = b * gr[0]; sf[3 * k + 1] = b * gr[1]; sf[3 * k + 2] = b * gr[2];
+                // (c0 + c1) + (c2 + 0): the order the one-thread version summed the channels in
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 1);
+                    dd[i] += __shfl_xor_sync(0xffffffffu, dd[i], 2);
+                }
+                if (c == 0) {
+                    float dxyz[3] = {0.f, 0.f, 0.f};
+                    if (live && a.sh_degree > 0) {       // through dir = v / |v|
+                        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
+                        const float dot = vx * dd[0] + vy * dd[1] + vz * dd[2];
+                        dxyz[0] = (s2 * dd[0] - vx * dot) * inv32;
+                        dxyz[1] = (s2 * dd[1] - vy * dot) * inv32;
+                        dxyz[2] = (s2 * dd[2] - vz * dot) * inv32;
+                    }
+                    sm.G[g * 16 + 11] = dxyz[0]; sm.G[g * 16 + 12] = dxyz[1]; sm.G[g * 16 + 13] = dxyz[2];
+                }
+                // overwrite this channel's third of the row with dL/dshs_final (every lane of the group has read its
+                // coefficients above: the shuffles are a convergence point of the warp)
+                if (c < 3) {
+                    for (int k = 0; k < 16; ++k) sf[3 * k + c] = (k < nb ? bs[k] : 0.f) * grc;
                 }
             }
             __syncthreads();
@@ -1089,10 +1123,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         if (n.w_d0) {
             float* Ad = SAVED ? abuf[6] : sm.A;
             float* Bd = SAVED ? abuf[7] : sm.B;
-            if (SAVED) {      // d0's layer arrived during the previous head; d2's goes where that head's tile was
-                S3G_FETCH_ACT(7);
-                pipe.release();
-                __syncthreads();
+            if (SAVED) {      // d2's layer arrived during the previous head; d0's (needed later) goes where that head's tile was
+                S3G_FETCH_ACT(6);
             } else {
                 tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
                 tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
@@ -1102,7 +1134,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
                 sm.Dout[tid] = (c < 3 && gi < a.P) ? ldz(a.g_feat, (size_t)gi * 3 + c) : 0.f;
             }
             __syncthreads();
-            small_head_backward(sm.Dout, 3, Bd, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS);
+            small_head_backward(sm.Dout, 3, Bd, HS, n.w_d4, part + a.off.d4w, part + a.off.d4b, sm.D2, HS, SAVED);
             dw_accum<64, 64, false>(sm.D2, HS, Ad, HS, part + a.off.d2w, part + a.off.d2b);
             tile_linear_T<64, 64, TL_ASSIGN_MASK>(sm.D2, HS, pipe, sm.D1, HS, Ad, HS);
             dw_accum<64, 64, false>(sm.D1, HS, sm.H, HS, part + a.off.d0w, part + a.off.d0b);

@@ -68,3 +68,31 @@ def test_render_signature_matches_reference():
     assert list(sig.parameters) == ["viewpoint_camera", "pc", "pipe", "bg_color", "scaling_modifier", "override_color",
                                     "stage", "return_decomposition", "return_dx", "render_feat"]
     assert sig.parameters["stage"].default == "fine" and sig.parameters["scaling_modifier"].default == 1.0
+
+
+def test_saved_activation_buffer_size_follows_the_enabled_heads(built_lib):
+    """s3g_deform_saved_bytes (host logic, no GPU): one [ceil(P/128)*128][64] float tile set per kept hidden layer -
+    h plus the hidden layer of every enabled head (the dino head has two) - and 0 for nets whose forward does not run
+    on the tcgen05 kernel (more than 4 levels)."""
+    import ctypes as C
+    from s3gaussian_b200 import _lib
+    from s3gaussian_b200.deformation import CNet
+    lib = _lib.load()
+
+    def saved(net, P):
+        byname = {n: p.detach() for n, p in net._named_hot_params()}
+        cnet = CNet()
+        net._fill(cnet, byname)
+        return int(lib.s3g_deform_saved_bytes(C.byref(cnet), P))
+
+    per_slot = lambda P: ((P + 127) // 128) * 128 * 64 * 4
+    default = make()                                        # pos + shs + dino: h, pos, shs, d0, d2
+    assert saved(default, 1000) == 5 * per_slot(1000)
+    assert saved(default, 128) == 5 * 128 * 64 * 4
+    assert saved(default, 0) == 0
+    allheads = make(no_ds=False, no_dr=False, no_do=False)  # + scales, rotation, opacity
+    assert saved(allheads, 1000) == 8 * per_slot(1000)
+    nofeat = make(feat_head=False, no_dshs=True)            # h + pos only
+    assert saved(nofeat, 300) == 2 * per_slot(300)
+    deep = make(reso=(8, 8, 8, 5), multires=(1, 2, 3, 4, 5))   # 5 levels: mma.sync forward, nothing kept
+    assert saved(deep, 1000) == 0

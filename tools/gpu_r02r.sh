@@ -13,3 +13,7 @@ DEV_P=500000 timeout 600 python tools/dev_deform.py --bwd --time --notest --reco
 echo "== per-kernel times (ncu launch list)"
 DEV_P=500000 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'deform_|hexplane_' -c 72 --csv --log-file $O/${T}_launches.csv python tools/dev_deform.py --bwd --time --notest > $O/${T}_launches.log 2>&1
 python tools/summarize_launches.py $O/${T}_launches.csv 1 2>&1 | head -9
+if [ "$2" = "ncu" ]; then
+echo "== ncu full of the backward decoder"
+DEV_P=500000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:deform_backward -s 2 -c 1 -o $O/${T}_dbwd python tools/dev_deform.py --bwd --time --notest > $O/${T}_dbwd.log 2>&1
+fi

@@ -44,7 +44,8 @@ def main():
             name = r[hdr.index('Kernel Name')].split('(')[0].replace('void ', '').split('<')[0]
             traffic.setdefault(name, {
                 'dram_bytes': int(nbytes(r, 'dram__bytes_read.sum') + nbytes(r, 'dram__bytes_write.sum')),
-                'duration_us': float(r[hdr.index('gpu__time_duration.sum')])})
+                'duration_us': float(r[hdr.index('gpu__time_duration.sum')]) *
+                               {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(units[hdr.index('gpu__time_duration.sum')], 1.0)})
     if traffic_path:
         json.dump({'source': f'{out} (ncu --set full --clock-control none, tools/dev_profile.py ours 2000000 1920 1280 '
                              'sh 1; first launch of each kernel)',

@@ -8,14 +8,18 @@ namespace {
 // prepared-weight table of the tcgen05 decoder
 void build_tc_table(const DNet& d, TcTable& t, TcPrepArgs* prep) {
     int off = 0;
-    auto put = [&](int id, const float* W, int N, int K) {
-        if (!W) { t.off[id] = -1; t.npad[id] = 0; t.k[id] = 0; if (prep) { prep->W[id] = nullptr; prep->n[id] = 0; } return; }
+    auto put = [&](int id, const float* W, int N, int K, int ld = 0) {
+        if (!W || K <= 0) { t.off[id] = -1; t.npad[id] = 0; t.k[id] = 0; if (prep) { prep->W[id] = nullptr; prep->n[id] = 0; prep->ld[id] = 0; } return; }
         const int np = (N + 15) & ~15;
         t.off[id] = off; t.npad[id] = np; t.k[id] = K;
         off += 2 * np * K;
-        if (prep) { prep->W[id] = W; prep->n[id] = N; }
+        if (prep) { prep->W[id] = W; prep->n[id] = N; prep->ld[id] = ld ? ld : K; }
     };
-    put(TL_FEAT, d.w_feat, 64, FD * d.L);
+    {   // the feature layer as two K-halves (deform_tc.cuh: TL_FEAT / TL_FEATB)
+        const int KF = FD * d.L, KA = KF < 64 ? KF : 64;
+        put(TL_FEAT, d.w_feat, 64, KA, KF);
+        put(TL_FEATB, d.w_feat ? d.w_feat + KA : nullptr, 64, KF - KA, KF);
+    }
     put(TL_POS1, d.pos.w1, 64, 64); put(TL_POS2, d.pos.w1 ? d.pos.w2 : nullptr, 3, 64);
     put(TL_SCL1, d.scl.w1, 64, 64); put(TL_SCL2, d.scl.w1 ? d.scl.w2 : nullptr, 3, 64);
     put(TL_ROT1, d.rot.w1, 64, 64); put(TL_ROT2, d.rot.w1 ? d.rot.w2 : nullptr, 4, 64);
@@ -24,11 +28,11 @@ void build_tc_table(const DNet& d, TcTable& t, TcPrepArgs* prep) {
     put(TL_D0, d.w_d0, 64, 64); put(TL_D2, d.w_d0 ? d.w_d2 : nullptr, 64, 64); put(TL_D4, d.w_d0 ? d.w_d4 : nullptr, 3, 64);
     t.total = off;
 }
-int deform_grid(int ntiles) {
+int deform_grid(int ntiles, int ctas_per_sm = 1) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int g = sms;      // one persistent CTA per SM (shared memory: weights double-buffered)
+    const int g = sms * ctas_per_sm;      // persistent CTAs, as many as are resident at once
     return ntiles < g ? ntiles : g;
 }
 }  // namespace
@@ -98,10 +102,11 @@ int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, 
         t.wprep = pp.dst;
         tc_prep_weights_kernel<<<dim3(8, TL_COUNT), 256, 0, stream>>>(pp);
         S3G_CUDA(cudaGetLastError(), "tc_prep_weights launch");
-        const size_t smem = (size_t)(2 * TCM * 128 + 2 * 64 * 128) * sizeof(float);
+        // operands [128][64] hi + lo, weights [64][64] hi + lo: 96 KB, two CTAs (and 2 x 256 TMEM columns) per SM
+        const size_t smem = (size_t)(2 * TCM * 64 + 2 * 64 * 64) * sizeof(float);
         S3G_CUDA(cudaFuncSetAttribute(deform_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform tc smem attr");
         const int ntiles = (P + TCM - 1) / TCM;
-        deform_forward_tc_kernel<<<deform_grid(ntiles), TCM, smem, stream>>>(t);
+        deform_forward_tc_kernel<<<deform_grid(ntiles, 2), TCM, smem, stream>>>(t);
     } else {
         if (acts) return fail(S3G_ERR_ARG, "deform_forward: this net's forward stores no activations (s3g_deform_saved_bytes == 0)");
         const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);

@@ -23,8 +23,10 @@ constexpr int TCM = 128;          // Gaussians per tile = UMMA M = TMEM lanes
 constexpr int TC_TMEM_COLS = 256;
 
 // layer ids in the prepared-weight table
+// (TL_FEAT / TL_FEATB: the feature layer is run as two K-halves, columns [0,64) and [64,32L) of its weight, so that no
+//  operand tile is wider than 64 columns: 96 KB of shared memory per CTA instead of 192 KB, two CTAs per SM)
 enum { TL_FEAT = 0, TL_POS1, TL_POS2, TL_SCL1, TL_SCL2, TL_ROT1, TL_ROT2, TL_OPA1, TL_OPA2, TL_SHS1, TL_SHS2,
-       TL_D0, TL_D2, TL_D4, TL_COUNT };
+       TL_D0, TL_D2, TL_D4, TL_FEATB, TL_COUNT };
 struct TcTable {
     int off[TL_COUNT];     // float offset of the layer's [hi | lo] block in the prepared buffer, -1 = absent
     int npad[TL_COUNT];    // rows padded to a multiple of 16
@@ -35,8 +37,9 @@ struct TcTable {
 // W [N][K] (PyTorch layout) -> canonical K-major tiles of its tf32 hi and lo parts, rows >= N zero.
 // One launch for all layers: blockIdx.y = layer.
 struct TcPrepArgs {
-    const float* W[TL_COUNT];
+    const float* W[TL_COUNT];   // first element of the (sub-)matrix
     int n[TL_COUNT];
+    int ld[TL_COUNT];           // row stride of the source matrix (= its full K)
     TcTable tab;
     float* dst;
 };
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const __grid_const
     float* dst = p.dst + p.tab.off[l];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NP * K; e += gridDim.x * blockDim.x) {
         const int n = e / K, k = e - n * K;
-        const float v = n < N ? __ldg(p.W[l] + (size_t)n * K + k) : 0.f;
+        const float v = n < N ? __ldg(p.W[l] + (size_t)n * p.ld[l] + k) : 0.f;
         uint32_t hi, lo;
         split_tf32_rna(v, hi, lo);
         const int ci = umma::canon_idx(n, k, K);
@@ -94,7 +97,8 @@ __device__ __forceinline__ void tc_fetch_weights(TcCtx& c, int layer) {   // thr
 // Runs the layer into TMEM columns [col, col+npad) and returns when the accumulators are readable;
 // meanwhile the weights of `next_layer` (or -1) start streaming into the weight buffer.
 // `keep` (or NULL): global destination of this layer's hi operand tile (128 x K floats), see DeformTcArgs::acts.
-__device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, int next_layer, float* keep = nullptr) {
+__device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, int next_layer, float* keep = nullptr,
+                                             bool accumulate = false) {
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -115,7 +119,7 @@ __device__ __forceinline__ void tc_run_layer(TcCtx& c, int layer, uint32_t col, 
             const uint32_t off = (uint32_t)(k0 / 4) * 128u;
             const uint64_t dah = umma::make_smem_desc(a_hi + off, 128, sbo), dal = umma::make_smem_desc(a_lo + off, 128, sbo);
             const uint64_t dbh = umma::make_smem_desc(b_hi + off, 128, sbo), dbl = umma::make_smem_desc(b_lo + off, 128, sbo);
-            umma::mma_tf32(c.tmem + col, dal, dbh, idesc, k0 > 0);
+            umma::mma_tf32(c.tmem + col, dal, dbh, idesc, accumulate || k0 > 0);
             umma::mma_tf32(c.tmem + col, dah, dbl, idesc, true);
             umma::mma_tf32(c.tmem + col, dah, dbh, idesc, true);
         }
@@ -173,7 +177,7 @@ __device__ __forceinline__ void tc_head2(TcCtx& c, int row, const float (&h)[64]
     umma::tmem_ld32(c.tmem + lane_base + 128, out);
 }
 
-__global__ void __launch_bounds__(TCM, 1) deform_forward_tc_kernel(const __grid_constant__ DeformTcArgs a) {
+__global__ void __launch_bounds__(TCM, 2) deform_forward_tc_kernel(const __grid_constant__ DeformTcArgs a) {
     extern __shared__ __align__(128) float s_dyn[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
@@ -182,9 +186,9 @@ __global__ void __launch_bounds__(TCM, 1) deform_forward_tc_kernel(const __grid_
     const int L = n.L, KF = FD * L;
     const int tid = threadIdx.x, warp = tid >> 5;
     TcCtx c;
-    c.op_hi = s_dyn;                        // [128][128] canonical
-    c.op_lo = s_dyn + TCM * 128;
-    c.w_sm = s_dyn + 2 * TCM * 128;         // [hi | lo], up to 2 x 64 x 128
+    c.op_hi = s_dyn;                        // [128][64] canonical
+    c.op_lo = s_dyn + TCM * 64;
+    c.w_sm = s_dyn + 2 * TCM * 64;          // [hi | lo], up to 2 x 64 x 64
     c.w_bar = &s_bar[0]; c.mma_bar = &s_bar[1];
     c.wph = 0; c.mph = 0;
     c.wprep = a.wprep; c.tab = &a.tab;
@@ -224,20 +228,31 @@ __global__ void __launch_bounds__(TCM, 1) deform_forward_tc_kernel(const __grid_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int gi = tile * TCM + tid;
         const bool valid = gi < a.P;
-        // ---- features -> operand (K = 32L): loads in batches of 16 x 16 B so they overlap -----
+        // ---- features -> operand, in two K-halves (columns [0,64) and [64,32L)); each half is 16 x 16 B loads in
+        //      flight per thread, the second half's are issued before the first half's MMAs are waited for
         {
             const float4* fr = reinterpret_cast<const float4*>(a.features + (size_t)(valid ? gi : 0) * KF);
-            for (int k0 = 0; k0 < KF; k0 += 64) {
-                float4 v[16];
+            const int KA = KF < 64 ? KF : 64, KB = KF - KA;
+            float4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                v[j] = (valid && 4 * j < KA) ? __ldg(fr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (4 * j < KA) tc_store4(c, tid, 4 * j, KA, v[j].x, v[j].y, v[j].z, v[j].w);
+            if (KB > 0) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    v[j] = (valid && k0 + 4 * j < KF) ? __ldg(fr + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j] = (valid && 4 * j < KB) ? __ldg(fr + 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tc_run_layer(c, TL_FEAT, 0, KB > 0 ? TL_FEATB : first_after_feat);
+            if (KB > 0) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (k0 + 4 * j < KF) tc_store4(c, tid, k0 + 4 * j, KF, v[j].x, v[j].y, v[j].z, v[j].w);
+                    if (4 * j < KB) tc_store4(c, tid, 4 * j, KB, v[j].x, v[j].y, v[j].z, v[j].w);
+                tc_run_layer(c, TL_FEATB, 0, first_after_feat, nullptr, true);
             }
         }
-        tc_run_layer(c, TL_FEAT, 0, first_after_feat);
         float h[64];
         tc_load_row64(c, 0, s_bias + TL_FEAT * 64, h);
         // where this tile's kept activations go; h is kept raw when the dino head (the one consumer of raw h) is on,

@@ -3,22 +3,22 @@
 //
 // Replaces ~150 PyTorch launches per render (24 F.grid_sample, 14 Linear/ReLU, poc_fre,
 // exp/normalize/sigmoid, eval_sh; scene/hexplane.py:73-106, scene/deformation.py:78-166,
-// gaussian_renderer/__init__.py:99-117) with one kernel each way:
+// gaussian_renderer/__init__.py:99-117) with two kernels each way:
 //
-//   tile of 64 Gaussians per CTA iteration (persistent grid)
-//   1. sample   one warp per Gaussian, lane = feature channel: each bilinear tap of the
-//               channels-last planes is ONE coalesced 128-byte load; the six plane
-//               samples of a level are multiplied in registers -> 32L features in smem
-//   2. decode   the dense layers run on the tensor cores as 3xTF32 (hi*hi + hi*lo + lo*hi,
-//               fp32 accumulate): 1e-4-relative parity with PyTorch fp32 rules out plain
-//               TF32/BF16 (~1e-3).  Activations never leave shared memory.
-//   3. finish   xyz+dx, exp/normalize/sigmoid, SH->RGB with the undeformed view direction,
-//               coalesced stores of the eight outputs.
-//
-// Backward recomputes 1-2 per tile (no [P,64] activations are ever stored), back-propagates
-// through the heads with the same MMA tiles, accumulates the Linear gradients in per-CTA
-// partial buffers (reduced by a second tiny kernel) and scatters plane gradients with
-// 128-byte-wide REDs.
+//   forward   hexplane_sample_kernel      four Gaussians per warp, lane = (Gaussian, channel quad): every bilinear
+//                                         corner of the channels-last planes is one LDG.128; the six plane samples
+//                                         of a level are multiplied in registers -> features [P][32L]
+//             deform_forward_tc_kernel    (deform_tc.cuh) the dense layers on tcgen05 / TMEM, 3xTF32 (hi*hi + hi*lo +
+//                                         lo*hi, fp32 accumulate: 1e-4-relative parity with PyTorch fp32 rules out
+//                                         plain TF32 / BF16, ~1e-3), xyz+dx, exp / normalize / sigmoid, SH->RGB with
+//                                         the undeformed view direction fused into the epilogues
+//             deform_forward_kernel       the same decoder on mma.sync, 64-row tiles (nets with more than 4 levels)
+//   backward  deform_backward_kernel      mma.sync 3xTF32, tiles of 64 Gaussians: the hidden activations come from
+//                                         what the tcgen05 forward kept (SAVED) or are recomputed from the features;
+//                                         push-back through the heads, Linear gradients into per-CTA partial buffers
+//                                         (deform_reduce_kernel sums them), dL/d(features) [P][32L]
+//             hexplane_scatter_kernel     plane gradients with 128-bit REDs (time planes: per-texel sums +
+//                                         hexplane_time_rows_kernel), d(xyz) through the bilinear weights
 #pragma once
 #include "../../include/s3g_b200.h"
 #include "common.cuh"
@@ -93,17 +93,6 @@ __device__ __forceinline__ void mma3_fold(float (&d)[NT][4], const float (&ds)[N
     for (int j = 0; j < NT; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[j][i] += ds[j][i];
-}
-
-// Stage a PyTorch-layout weight [N][K] (row n contiguous) into smem rows of stride K+4.
-template <int K>
-__device__ __forceinline__ void stage_weight(const float* __restrict__ Wg, int N, float* sW) {
-    constexpr int WS = K + 4;
-    for (int i = threadIdx.x; i < N * (K / 4); i += DTHREADS) {
-        const int n = i / (K / 4), k4 = i - n * (K / 4);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(Wg + (size_t)n * K) + k4);
-        *reinterpret_cast<float4*>(&sW[n * WS + 4 * k4]) = v;
-    }
 }
 
 // ---- double-buffered weight staging -------------------------------------------------

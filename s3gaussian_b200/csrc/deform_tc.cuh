@@ -12,7 +12,11 @@
 //   * one thread issues the K/8 x 3 UMMAs of a layer and commits them to an mbarrier;
 //   * the epilogue is a TMEM -> register load of the thread's own row: bias, ReLU, split, store
 //     - no cross-thread traffic; the per-Gaussian outputs (xyz+dx, exp/normalize/sigmoid,
-//     SH->RGB) are finished in the same registers.
+//     SH->RGB) are finished in the same registers;
+//   * no operand tile is wider than 64 columns (the feature layer runs as two K-halves), so a CTA needs 96 KB of
+//     shared memory and 256 TMEM columns: two CTAs per SM hide each other's MMA -> commit -> wait latency;
+//   * for training, every hidden layer's operand tile is also copied to global memory by one bulk async copy
+//     (DeformTcArgs::acts) - the backward kernel reads those instead of recomputing the layers.
 #pragma once
 #include "deform.cuh"
 #include "umma.cuh"

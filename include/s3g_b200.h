@@ -347,9 +347,7 @@ size_t s3g_deform_forward_workspace_bytes(const s3g_deform_net* net);
 /* Training variant: the same forward, which also keeps the decoder's hidden activations (h = feature_out(f) and the
  * hidden layer of every enabled head, scene/deformation.py:56-76 - what autograd keeps for the reference) in the
  * opaque buffer `acts` of s3g_deform_saved_bytes(net, P) bytes, so that s3g_deform_backward_saved does not
- * recompute them.  s3g_deform_saved_bytes is 0 for nets whose forward does not run on the tcgen05 kernel (more
- * than 4 levels); such nets use s3g_deform_forward / s3g_deform_backward.  acts == NULL: identical to
- * s3g_deform_forward. */
+ * recompute them.  acts == NULL: identical to s3g_deform_forward.  (1 <= num_levels <= 4; feat_dim 32; width 64.) */
 size_t s3g_deform_saved_bytes(const s3g_deform_net* net, int P);
 int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, const float* scales,
                             const float* rotations, const float* opacity, const float* shs, float time,

@@ -56,7 +56,7 @@ int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (P < 0) return fail(S3G_ERR_ARG, "deform_forward: P < 0");
     if (P == 0) return S3G_OK;
-    DeformFwdArgs a;
+    struct { DNet net; } a;
     int rc = to_dnet(net, a.net);
     if (rc != S3G_OK) return rc;
     if (!xyz || !scales || !rotations || !opacity || !shs || !campos)
@@ -64,11 +64,6 @@ int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, 
     if (!means3D || !scales_act || !rot_act || !opacity_act || !colors || !features)
         return fail(S3G_ERR_ARG, "deform_forward: null output");
     if (sh_degree < 0 || sh_degree > 3) return fail(S3G_ERR_ARG, "deform_forward: sh_degree must be 0..3");
-    a.P = P; a.xyz = xyz; a.scales = scales; a.rot = rotations; a.opacity = opacity; a.shs = shs;
-    a.campos = campos; a.time = time; a.sh_degree = sh_degree;
-    a.o_means = means3D; a.o_scales = scales_act; a.o_rot = rot_act; a.o_opacity = opacity_act;
-    a.o_colors = colors; a.o_dx = dx; a.o_dshs = dshs; a.o_feat = feat; a.features = features;
-    build_wseq(a.net, false, a.wseq);
     {
         SampleArgs sa;
         sa.net = a.net; sa.P = P; sa.xyz = xyz; sa.time = time; sa.features = features;
@@ -80,7 +75,7 @@ int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, 
         else hexplane_sample_kernel<0><<<blocks, 256, 0, stream>>>(sa);
         S3G_CUDA(cudaGetLastError(), "hexplane_sample launch");
     }
-    if (a.net.L <= 4) {
+    {
         // ---- decoder on the 5th-gen tensor cores (tcgen05 / TMEM) ------------------------------
         if (!workspace) return fail(S3G_ERR_ARG, "deform_forward: null workspace");
         DeformTcArgs t;
@@ -107,12 +102,6 @@ int s3g_deform_forward_save(const s3g_deform_net* net, int P, const float* xyz, 
         S3G_CUDA(cudaFuncSetAttribute(deform_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform tc smem attr");
         const int ntiles = (P + TCM - 1) / TCM;
         deform_forward_tc_kernel<<<deform_grid(ntiles, 2), TCM, smem, stream>>>(t);
-    } else {
-        if (acts) return fail(S3G_ERR_ARG, "deform_forward: this net's forward stores no activations (s3g_deform_saved_bytes == 0)");
-        const size_t smem = DeformSmem::floats(a.net.L) * sizeof(float);
-        const int ntiles = (P + DT - 1) / DT;
-        S3G_CUDA(cudaFuncSetAttribute(deform_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "deform smem attr");
-        deform_forward_kernel<0><<<deform_grid(ntiles), DTHREADS, smem, stream>>>(a);
     }
     S3G_CUDA(cudaGetLastError(), "deform_forward launch");
     return S3G_OK;

@@ -12,7 +12,6 @@
 //                                         lo*hi, fp32 accumulate: 1e-4-relative parity with PyTorch fp32 rules out
 //                                         plain TF32 / BF16, ~1e-3), xyz+dx, exp / normalize / sigmoid, SH->RGB with
 //                                         the undeformed view direction fused into the epilogues
-//             deform_forward_kernel       the same decoder on mma.sync, 64-row tiles (nets with more than 4 levels)
 //   backward  deform_backward_kernel      mma.sync 3xTF32, tiles of 64 Gaussians: the hidden activations come from
 //                                         what the tcgen05 forward kept (SAVED) or are recomputed from the features;
 //                                         push-back through the heads, Linear gradients into per-CTA partial buffers
@@ -310,17 +309,6 @@ __device__ __forceinline__ int sh_basis16(int deg, float x, float y, float z, fl
     return 16;
 }
 
-struct DeformFwdArgs {
-    DNet net;
-    int P;
-    const float *xyz, *scales, *rot, *opacity, *shs, *campos;
-    float time;
-    int sh_degree;
-    float *o_means, *o_scales, *o_rot, *o_opacity, *o_colors, *o_dx, *o_dshs, *o_feat;
-    float* features;     // [P][32L] written by hexplane_sample_kernel, read by the decoder tiles
-    WSeq wseq;           // weight matrices in the order the tile uses them
-};
-
 // ---- stage 1: HexPlane sampling, one warp per Gaussian, high occupancy ---------------
 // The gather (12 KB of texels per Gaussian, L2-resident planes) is latency-bound unless many
 // warps keep loads in flight, which the shared-memory-heavy decoder CTAs cannot; it is its own
@@ -406,146 +394,6 @@ __device__ __forceinline__ void tile_rows_store(float* __restrict__ gdst, int g0
             *(reinterpret_cast<float4*>(gdst + (size_t)(g0 + g) * FL) + c4) = *reinterpret_cast<const float4*>(sSrc + g * FS + 4 * c4);
     }
 }
-
-// smem carve (floats).  FS = 32L+4.
-struct DeformSmem {
-    float *F, *H, *A, *B, *W, *S, *Dsh, *X;
-    __device__ DeformSmem(float* base, int L) {
-        const int FS = FD * L + 4;
-        F = base;                         // [64][FS]   features, dead after h; A and B alias it
-        A = F;                            // [64][HS]
-        B = F + DT * HS;                  // [64][HS]   (needs 2*HS <= FS, i.e. L >= 4, else separate: see host sizing)
-        H = base + DT * (FS > 2 * HS ? FS : 2 * HS);      // [64][HS]
-        W = H + DT * HS;                  // 2 x [64][max(FS,HS)] weight staging (double-buffered)
-        S = W + 2 * HWID * (FS > HS ? FS : HS);           // [64][16] small head outputs
-        Dsh = S + DT * 16;                // [64][52] dshs / shs_final
-        X = Dsh + DT * 52;                // [64][4] xyz of the tile
-    }
-    __host__ __device__ static size_t floats(int L) {
-        const int FS = FD * L + 4;
-        return (size_t)DT * (FS > 2 * HS ? FS : 2 * HS) + DT * HS + 2 * HWID * (FS > HS ? FS : HS) + DT * 16 + DT * 52 + DT * 4;
-    }
-};
-// columns of the small-output tile S
-constexpr int S_DX = 0, S_DS = 3, S_DR = 6, S_DO = 10, S_FEAT = 11;
-
-template <int LT>   // LT = 4: compile-time level count (K of the first layer = 128); 0: generic via K=32*L switch
-__global__ void __launch_bounds__(DTHREADS, 1) deform_forward_kernel(const __grid_constant__ DeformFwdArgs a) {
-    extern __shared__ __align__(16) float s_dyn[];
-    const DNet& n = a.net;
-    const int L = n.L;
-    const int FS = FD * L + 4;
-    DeformSmem sm(s_dyn, L);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntiles = (a.P + DT - 1) / DT;
-    __shared__ WSeq s_seq;
-    WPipe pipe;
-    pipe.start(a.wseq, &s_seq, sm.W, sm.W + HWID * (FS > HS ? FS : HS));
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int g0 = tile * DT;
-        // ---- tile inputs ---------------------------------------------------
-        if (tid < DT * 3) {
-            const int g = tid / 3, c = tid - 3 * g;
-            sm.X[g * 4 + c] = (g0 + g < a.P) ? a.xyz[(size_t)(g0 + g) * 3 + c] : 0.f;
-        }
-        __syncthreads();
-        // ---- 1. features of the tile (sampled by hexplane_sample_kernel) ---------
-        tile_rows_load(a.features, g0, a.P, FD * L, sm.F, FS);
-        __syncthreads();
-        // ---- 2. decoder ------------------------------------------------------
-        // h = feature_out(f)
-        if (LT == 4 || L == 4) tile_linear<128, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        // zero the small outputs (disabled heads contribute 0)
-        for (int i = tid; i < DT * 16; i += DTHREADS) sm.S[i] = 0.f;
-        __syncthreads();
-        if (n.pos.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.pos.b1, sm.A, HS);
-            tile_small_out(sm.A, HS, n.pos.w2, n.pos.b2, 3, sm.S, 16, S_DX);
-        }
-        if (n.scl.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.scl.b1, sm.B, HS);
-            tile_small_out(sm.B, HS, n.scl.w2, n.scl.b2, 3, sm.S, 16, S_DS);
-        }
-        __syncthreads();
-        if (n.rot.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.rot.b1, sm.A, HS);
-            tile_small_out(sm.A, HS, n.rot.w2, n.rot.b2, 4, sm.S, 16, S_DR);
-        }
-        if (n.opa.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.opa.b1, sm.B, HS);
-            tile_small_out(sm.B, HS, n.opa.w2, n.opa.b2, 1, sm.S, 16, S_DO);
-        }
-        __syncthreads();
-        if (n.shs.w1) {
-            tile_linear<64, 64, true, true>(sm.H, HS, pipe, n.shs.b1, sm.A, HS);
-            tile_linear<64, 48, false, false>(sm.A, HS, pipe, n.shs.b2, sm.Dsh, 52);
-        } else {
-            for (int i = tid; i < DT * 52; i += DTHREADS) sm.Dsh[i] = 0.f;
-            __syncthreads();
-        }
-        if (n.w_d0) {   // dino head: Linear, ReLU, Linear, ReLU, Linear - no leading ReLU (deformation.py:70-76)
-            tile_linear<64, 64, false, true>(sm.H, HS, pipe, n.b_d0, sm.A, HS);
-            tile_linear<64, 64, false, true>(sm.A, HS, pipe, n.b_d2, sm.B, HS);
-            tile_small_out(sm.B, HS, n.w_d4, n.b_d4, 3, sm.S, 16, S_FEAT);
-        }
-        __syncthreads();
-        // ---- 3. finish ---------------------------------------------------------
-        // dshs out (coalesced) and shs_final = shs + dshs kept in smem
-        for (int e = tid; e < DT * 48; e += DTHREADS) {
-            const int g = e / 48, j = e - 48 * g;
-            if (g0 + g < a.P) {
-                const float d = sm.Dsh[g * 52 + j];
-                if (a.o_dshs) a.o_dshs[(size_t)(g0 + g) * 48 + j] = d;
-                sm.Dsh[g * 52 + j] = a.shs[(size_t)(g0 + g) * 48 + j] + d;
-            }
-        }
-        __syncthreads();
-        {
-            const int g = tid >> 2, c = tid & 3;
-            const int gi = g0 + g;
-            if (g < DT && gi < a.P) {
-                const float* S = sm.S + g * 16;
-                if (c < 3) {
-                    const float p = sm.X[g * 4 + c];
-                    const float d = S[S_DX + c];
-                    a.o_means[(size_t)gi * 3 + c] = p + d;                                  // pts*mask + dx, mask == 1
-                    if (a.o_dx) a.o_dx[(size_t)gi * 3 + c] = d;
-                    if (a.o_feat) a.o_feat[(size_t)gi * 3 + c] = S[S_FEAT + c];
-                    a.o_scales[(size_t)gi * 3 + c] = expf(a.scales[(size_t)gi * 3 + c] + S[S_DS + c]);
-                    // SH -> RGB with the UNDEFORMED position (gaussian_renderer/__init__.py:110)
-                    float dx_ = sm.X[g * 4 + 0] - a.campos[0], dy_ = sm.X[g * 4 + 1] - a.campos[1],
-                          dz_ = sm.X[g * 4 + 2] - a.campos[2];
-                    const float inv = 1.0f / sqrtf(dx_ * dx_ + dy_ * dy_ + dz_ * dz_);
-                    float bs[16];
-                    const int nb = sh_basis16(a.sh_degree, dx_ * inv, dy_ * inv, dz_ * inv, bs);
-                    float r = 0.f;
-                    for (int k = 0; k < nb; ++k) r = fmaf(bs[k], sm.Dsh[g * 52 + 3 * k + c], r);
-                    a.o_colors[(size_t)gi * 3 + c] = fmaxf(r + 0.5f, 0.0f);
-                } else {
-                    // rotation (normalize, eps 1e-12) and opacity (sigmoid)
-                    float q[4], nn = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        q[i] = a.rot[(size_t)gi * 4 + i] + S[S_DR + i];
-                        nn += q[i] * q[i];
-                    }
-                    const float invn = 1.0f / fmaxf(sqrtf(nn), 1e-12f);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) a.o_rot[(size_t)gi * 4 + i] = q[i] * invn;
-                    const float o = a.opacity[gi] + S[S_DO];
-                    a.o_opacity[gi] = 1.0f / (1.0f + expf(-o));
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 
 // =============================================================================
 // Backward
@@ -848,7 +696,6 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         else if (L == 1) tile_linear<32, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         else if (L == 2) tile_linear<64, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         else if (L == 3) tile_linear<96, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
-        else if (L == 8) tile_linear<256, 64, false, false>(sm.F, FS, pipe, n.b_feat, sm.H, HS);
         }
 
         // ---- per-Gaussian activation backward -> small deltas in G[g][0..10] ----
@@ -1135,7 +982,6 @@ __global__ void __launch_bounds__(DTHREADS, 1) deform_backward_kernel(const __gr
         else if (L == 1) feat_layers_bwd<32>(sm, n, part, a.off, FS, pipe);
         else if (L == 2) feat_layers_bwd<64>(sm, n, part, a.off, FS, pipe);
         else if (L == 3) feat_layers_bwd<96>(sm, n, part, a.off, FS, pipe);
-        else if (L == 8) feat_layers_bwd<256>(sm, n, part, a.off, FS, pipe);
         // DF now lives in sm.A with row stride FS: hand it to the scatter kernel, and write the
         // part of d_xyz that does not go through the planes (identity path + SH view direction)
         tile_rows_store(a.dfeatures, g0, a.P, FD * L, sm.A, FS);

@@ -18,9 +18,10 @@ inline int to_dnet(const s3g_deform_net* n, DNet& d) {
     if (!n) return fail(S3G_ERR_ARG, "deform: null net");
     if (n->feat_dim != FD) return fail(S3G_ERR_UNSUPPORTED, "deform: output_coordinate_dim must be 32");
     if (n->width != HWID) return fail(S3G_ERR_UNSUPPORTED, "deform: net_width must be 64");
-    if (!(n->num_levels == 1 || n->num_levels == 2 || n->num_levels == 3 || n->num_levels == 4 ||
-          n->num_levels == 8))
-        return fail(S3G_ERR_UNSUPPORTED, "deform: number of HexPlane levels must be 1, 2, 3, 4 or 8");
+    // (8 levels were accepted up to round 2 but could never launch: 64-row tiles of 256 features need 235 KB of
+    //  shared memory.  The reference's own configs use 4: multires [1,2,4,8], arguments/__init__.py:215.)
+    if (n->num_levels < 1 || n->num_levels > 4)
+        return fail(S3G_ERR_UNSUPPORTED, "deform: number of HexPlane levels (len(multires)) must be 1..4");
     d.L = n->num_levels;
     for (int l = 0; l < d.L; ++l) {
         for (int c = 0; c < 4; ++c) {
@@ -76,12 +77,10 @@ inline void build_wseq(const DNet& d, bool backward, WSeq& q, bool saved = false
 }
 
 // Hidden activations the tcgen05 forward can keep for the backward: [slot][P][64] floats, one slot per enabled
-// kind in this order.  Returns the slot count and fills slot[kind] (-1 = absent).  0 when the forward that
-// runs for this net (L > 4: the mma.sync kernel) does not store them.
+// kind in this order.  Returns the slot count and fills slot[kind] (-1 = absent).
 enum { AK_H = 0, AK_POS, AK_SCL, AK_ROT, AK_OPA, AK_SHS, AK_D0, AK_D2, AK_COUNT };
 inline int act_slots(const DNet& d, int (&slot)[AK_COUNT]) {
     for (int i = 0; i < AK_COUNT; ++i) slot[i] = -1;
-    if (d.L > 4) return 0;
     int n = 0;
     slot[AK_H] = n++;
     if (d.pos.w1) slot[AK_POS] = n++;

@@ -73,7 +73,7 @@ def test_render_signature_matches_reference():
 def test_saved_activation_buffer_size_follows_the_enabled_heads(built_lib):
     """s3g_deform_saved_bytes (host logic, no GPU): one [ceil(P/128)*128][64] float tile set per kept hidden layer -
     h plus the hidden layer of every enabled head (the dino head has two) - and 0 for nets whose forward does not run
-    on the tcgen05 kernel (more than 4 levels)."""
+    on the tcgen05 kernel (unsupported level counts)."""
     import ctypes as C
     from s3gaussian_b200 import _lib
     from s3gaussian_b200.deformation import CNet
@@ -94,5 +94,5 @@ def test_saved_activation_buffer_size_follows_the_enabled_heads(built_lib):
     assert saved(allheads, 1000) == 8 * per_slot(1000)
     nofeat = make(feat_head=False, no_dshs=True)            # h + pos only
     assert saved(nofeat, 300) == 2 * per_slot(300)
-    deep = make(reso=(8, 8, 8, 5), multires=(1, 2, 3, 4, 5))   # 5 levels: mma.sync forward, nothing kept
+    deep = make(reso=(8, 8, 8, 5), multires=(1, 2, 3, 4, 5))   # 5 levels: not a supported net -> 0, and the forward raises
     assert saved(deep, 1000) == 0

@@ -69,6 +69,61 @@ def test_fused_deform_matches_reference_golden(path, saved, built_lib, monkeypat
     assert checked >= 28
 
 
+@pytest.mark.parametrize("saved", [True, False], ids=["saved_activations", "recompute"])
+@pytest.mark.parametrize("L", [1, 2, 3, 4])
+def test_level_counts_against_the_oracle(L, saved, built_lib, monkeypatch):
+    """1 .. 4 HexPlane levels (the level counts the kernels accept; feature widths 32 .. 128): the tcgen05 forward
+    runs the feature layer as K-halves of 32+0, 64+0, 64+32 and 64+64 columns, the backward's generic-L
+    instantiations cover 1 .. 3.  Forward
+    outputs and every gradient against oracle/deform_oracle.py (float64 torch autograd), all heads enabled."""
+    from oracle import deform_oracle as do
+    from s3gaussian_b200 import deformation, synthetic as syn
+    from s3gaussian_b200.deformation import deform_network
+    monkeypatch.setattr(deformation, "SAVE_ACTIVATIONS", saved)
+    reso, multires = (12, 10, 8, 6), tuple(range(1, L + 1))
+    aabb = ((9.0, 4.0, 3.0), (-2.0, -4.0, -3.0))
+    flags = dict(no_ds=False, no_dr=False, no_do=False)
+    st = syn.make_deform_state(5 + L, reso, multires, aabb=aabb, weight_scale=0.2)
+    net = deform_network(ref_ext.ref_deform_args(reso, multires, **flags))
+    net.deformation_net.set_aabb(list(aabb[0]), list(aabb[1]))
+    missing, unexpected = net.load_state_dict(st, strict=False)
+    assert not unexpected
+    net = net.to(DEV)
+    P = 333                                   # not a multiple of 64 / 128: ragged last tile
+    g = torch.Generator().manual_seed(L)
+    lo, hi = torch.tensor(aabb[1]), torch.tensor(aabb[0])
+    xyz = lo + (hi - lo) * torch.rand(P, 3, generator=g)
+    sc, ro, op = torch.randn(P, 3, generator=g) * 0.3 - 2, torch.randn(P, 4, generator=g), torch.randn(P, 1, generator=g)
+    shs = torch.randn(P, 16, 3, generator=g) * 0.3
+    campos = torch.tensor([0.3, -0.2, 6.0])
+    t = 0.37
+    ws = [torch.randn(*shape, generator=g) for shape in ((P, 3), (P, 3), (P, 4), (P, 1), (P, 3), (P, 3), (P, 16, 3), (P, 3))]
+    # ours
+    leaves = [v.clone().to(DEV).requires_grad_(True) for v in (xyz, sc, ro, op, shs)]
+    outs = net.render_front(*leaves, t, campos.to(DEV), 3)
+    sum((o * w.to(DEV)).sum() for o, w in zip(outs, ws)).backward()
+    # oracle, float64
+    std = {k: v.double().requires_grad_(v.is_floating_point() and "grid.aabb" not in k) for k, v in st.items()}
+    ol = [v.clone().double().requires_grad_(True) for v in (xyz, sc, ro, op, shs)]
+    d = do.deform_forward(std, ol[0], ol[1], ol[2], ol[3], ol[4], torch.full((P, 1), t, dtype=torch.float64),
+                          no_dx=False, no_ds=False, no_dr=False, no_do=False, no_dshs=False, feat_head=True)
+    front = do.render_front(ol[0], d, campos.double(), 3)
+    ref_outs = (d["means3D"], front["scales"], front["rotations"], front["opacity"], front["colors_precomp"], d["dx"],
+                d["dshs"], d["feat"])
+    sum((o * w.double()).sum() for o, w in zip(ref_outs, ws)).backward()
+    for o, r, n in zip(outs, ref_outs, ("means3D", "scales", "rot", "opacity", "colors", "dx", "dshs", "feat")):
+        assert rel(o.detach().cpu().numpy(), r.detach().numpy().reshape(o.shape)) < TOL, (L, n)
+    for a, b, n in zip(leaves, ol, ("xyz", "scales", "rot", "opacity", "shs")):
+        assert rel(a.grad.cpu().numpy(), b.grad.numpy()) < TOL, (L, "d_" + n)
+    checked = 0
+    for k, p in net.named_parameters():
+        if p.grad is None or k not in std or std[k].grad is None:
+            continue
+        assert rel(p.grad.cpu().numpy(), std[k].grad.numpy().reshape(p.shape)) < TOL, (L, k)
+        checked += 1
+    assert checked >= 6 * L + 20
+
+
 def _small_fine_scene(P=400, W=80, H=48, seed=3):
     from s3gaussian_b200 import synthetic as syn
     from s3gaussian_b200.deformation import deform_network
